@@ -1,0 +1,837 @@
+// engine.cu -- the DorPatch hot-path engine behind include/dorpatch.h.
+//
+// One engine per GPU.  It owns: the standardised classifier weights (ResNetV2-50x1-BiT,
+// NHWC/KRSC), a workspace arena sized for `chunk` EOT samples, cuDNN + cublasLt handles.
+// The classifier's 3x3 / 7x7 convolutions run on tensor cores through cuDNN, the 1x1
+// convolutions (36 of 53) are plain NHWC GEMMs through cublasLt (the residual add is fused
+// as the GEMM's C operand); everything else is the hand-written kernels of kernels_*.cu.
+// Backward is data-gradient only (the weights are frozen during the attack; the reference's
+// unused weight-gradient, SURVEY quirk Q7, is not computed).
+#include <cublasLt.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cudnn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <initializer_list>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/dorpatch.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+[[noreturn]] void fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  throw std::runtime_error(buf);
+}
+
+#define CUDA_OK(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) fail("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  } while (0)
+#define CUDNN_OK(expr)                                                                             \
+  do {                                                                                             \
+    cudnnStatus_t _s = (expr);                                                                     \
+    if (_s != CUDNN_STATUS_SUCCESS) fail("cuDNN error %d (%s) at %s:%d [%s]", (int)_s, cudnnGetErrorString(_s), __FILE__, __LINE__, #expr); \
+  } while (0)
+#define CUBLAS_OK(expr)                                                                            \
+  do {                                                                                             \
+    cublasStatus_t _s = (expr);                                                                    \
+    if (_s != CUBLAS_STATUS_SUCCESS) fail("cuBLASLt error %d at %s:%d [%s]", (int)_s, __FILE__, __LINE__, #expr); \
+  } while (0)
+#define KERNEL_OK() CUDA_OK(cudaGetLastError())
+
+constexpr int DEPTHS[4] = {3, 4, 6, 3};
+constexpr int WIDTHS[4] = {256, 512, 1024, 2048};
+constexpr int STEM_CH = 64;
+constexpr int UNIT = 7;   // basic_unit of the group lasso / patch selection (attack.py:52)
+
+struct ConvW {            // one convolution's weights (device, KRSC, activation dtype)
+  int cin = 0, cin_pad = 0, cout = 0, k = 1, stride = 1, pad = 0;
+  void* w = nullptr;
+  cudnnFilterDescriptor_t wdesc = nullptr;
+  cudnnConvolutionDescriptor_t cdesc = nullptr;
+};
+struct GNW { int C = 0; float* gamma = nullptr; float* beta = nullptr; };
+struct Block {
+  int cin, mid, cout, stride, hin, hout;
+  bool has_ds;
+  GNW n1, n2, n3;
+  ConvW ds, c1, c2, c3;
+  // saved tensors / stats for backward (device, per chunk)
+  void* h1 = nullptr; void* h2 = nullptr; void* out = nullptr;
+  float* st1 = nullptr; float* st2 = nullptr; float* st3 = nullptr;
+};
+
+struct CudnnPlan {
+  cudnnTensorDescriptor_t xdesc = nullptr, ydesc = nullptr;
+  cudnnConvolutionFwdAlgo_t fwd_algo; cudnnMathType_t fwd_math; size_t fwd_ws = 0; bool fwd_ready = false;
+  cudnnConvolutionBwdDataAlgo_t bwd_algo; cudnnMathType_t bwd_math; size_t bwd_ws = 0; bool bwd_ready = false;
+};
+struct GemmPlan {
+  cublasLtMatmulDesc_t op = nullptr;
+  cublasLtMatrixLayout_t a = nullptr, b = nullptr, c = nullptr;
+  cublasLtMatmulAlgo_t algo;
+};
+
+}  // namespace
+
+struct dp_engine {
+  dp_config cfg;
+  bool bf16 = false;
+  size_t es = 4;            // activation element size
+  int Cp = 4;               // padded input channels
+  int H = 224, K = 1000, chunk = 64;
+  int num_sms = 148;
+  cudnnHandle_t cudnn = nullptr;
+  cublasLtHandle_t lt = nullptr;
+  cudnnDataType_t cudnn_dt = CUDNN_DATA_FLOAT;
+  cudaDataType_t cuda_dt = CUDA_R_32F;
+  cublasComputeType_t lt_compute = CUBLAS_COMPUTE_32F;
+  int64_t device_bytes = 0, launches = 0;
+  std::vector<void*> allocs;
+  bool weights_loaded = false;
+
+  ConvW stem;
+  std::vector<Block> blocks;
+  GNW head_gn;
+  float* fc_w = nullptr; float* fc_b = nullptr;
+
+  // workspace (sized for `chunk` samples)
+  void* net_in = nullptr;          // [chunk,H,H,Cp]
+  void* act = nullptr;             // scratch activation (stem out / GN outputs)
+  void* act2 = nullptr;            // scratch (subsampled shortcut input)
+  void* x0 = nullptr;              // pooled stem output (saved)
+  int8_t* pool_amax = nullptr;
+  void* g[4] = {nullptr, nullptr, nullptr, nullptr};   // gradient scratch
+  float* gn_partial = nullptr;
+  float* head_stats = nullptr;
+  float* pooled = nullptr; float* dpooled = nullptr;
+  float* logits = nullptr; float* dlogits = nullptr;
+  void* d_input = nullptr;         // result of backward: [n,H,H,Cp]
+  void* lib_ws = nullptr; size_t lib_ws_bytes = 0;
+
+  // per-image buffers (max_images)
+  float* adv_x = nullptr; float* dLs = nullptr; float* scale = nullptr; float* l2 = nullptr;
+  float* loss_struc = nullptr; float* loss_density = nullptr; float* group_lasso = nullptr;
+  float* win_dev = nullptr; float* grp_ss = nullptr;
+  float* lr_d = nullptr; float* structured_d = nullptr; float* coeff_d = nullptr;
+  float* host_x = nullptr; float* host_mask = nullptr; float* host_pattern = nullptr; float* host_G = nullptr;  // dp_attack_step_host
+
+  // per-sample buffers (grown on demand)
+  int cap_samples = 0;
+  int16_t* rects_d = nullptr; int32_t* y_d = nullptr; uint8_t* tg_d = nullptr;
+  float* loss_d = nullptr; int32_t* preds_d = nullptr;
+  // pinned staging
+  unsigned char* pin = nullptr; size_t pin_bytes = 0;
+
+  std::map<std::pair<int, int>, CudnnPlan> cudnn_plans;                 // (layer id, N)
+  std::map<std::tuple<int, int, int, int>, GemmPlan> gemm_plans;        // (rows, n_out, k, mode)
+
+  // ---------------------------------------------------------------------------------
+  void* dmalloc(size_t bytes) {
+    void* p = nullptr;
+    bytes = (bytes + 255) / 256 * 256;
+    if (bytes == 0) bytes = 256;
+    CUDA_OK(cudaMalloc(&p, bytes));
+    allocs.push_back(p);
+    device_bytes += (int64_t)bytes;
+    return p;
+  }
+  void ensure_pin(size_t bytes) {
+    if (bytes <= pin_bytes) return;
+    if (pin) cudaFreeHost(pin);
+    pin_bytes = std::max(bytes, (size_t)1 << 20);
+    CUDA_OK(cudaMallocHost((void**)&pin, pin_bytes));
+  }
+  void ensure_samples(int n) {
+    if (n <= cap_samples) return;
+    // (old buffers stay in `allocs` and are released at destroy)
+    cap_samples = std::max(n, cap_samples * 2);
+    rects_d = (int16_t*)dmalloc((size_t)cap_samples * 16 * sizeof(int16_t));
+    y_d = (int32_t*)dmalloc((size_t)cap_samples * sizeof(int32_t));
+    tg_d = (uint8_t*)dmalloc((size_t)cap_samples);
+    loss_d = (float*)dmalloc((size_t)cap_samples * sizeof(float));
+    preds_d = (int32_t*)dmalloc((size_t)cap_samples * sizeof(int32_t));
+  }
+
+  // ---- geometry -----------------------------------------------------------------------
+  int Hs() const { return H / 2; }
+  int Hp() const { return H / 4; }
+  size_t max_act_elems() const {   // per sample
+    size_t m = (size_t)Hs() * Hs() * STEM_CH;
+    for (auto& b : blocks) {
+      m = std::max(m, (size_t)b.hin * b.hin * std::max(b.cin, b.mid));
+      m = std::max(m, (size_t)b.hout * b.hout * b.cout);
+    }
+    m = std::max(m, (size_t)H * H * Cp);
+    return m;
+  }
+
+  void build_arch() {
+    int cin = STEM_CH, h = Hp();
+    for (int s = 0; s < 4; ++s) {
+      for (int bi = 0; bi < DEPTHS[s]; ++bi) {
+        Block b{};
+        b.cin = cin; b.cout = WIDTHS[s]; b.mid = b.cout / 4;
+        b.stride = (bi == 0 && s > 0) ? 2 : 1;
+        b.hin = h; b.hout = (h + b.stride - 1) / b.stride;
+        b.has_ds = (bi == 0);
+        blocks.push_back(b);
+        cin = b.cout; h = b.hout;
+      }
+    }
+  }
+
+  void make_conv(ConvW& c, int cin, int cout, int k, int stride, int pad, int cin_pad) {
+    c.cin = cin; c.cin_pad = cin_pad; c.cout = cout; c.k = k; c.stride = stride; c.pad = pad;
+    c.w = dmalloc((size_t)cout * k * k * cin_pad * es);
+    if (k > 1) {   // cuDNN path
+      CUDNN_OK(cudnnCreateFilterDescriptor(&c.wdesc));
+      CUDNN_OK(cudnnSetFilter4dDescriptor(c.wdesc, cudnn_dt, CUDNN_TENSOR_NHWC, cout, cin_pad, k, k));
+      CUDNN_OK(cudnnCreateConvolutionDescriptor(&c.cdesc));
+      CUDNN_OK(cudnnSetConvolution2dDescriptor(c.cdesc, pad, pad, stride, stride, 1, 1, CUDNN_CROSS_CORRELATION, CUDNN_DATA_FLOAT));
+      CUDNN_OK(cudnnSetConvolutionMathType(c.cdesc, default_math()));
+    }
+  }
+  cudnnMathType_t default_math() const {
+    if (cfg.precision == DP_PREC_FP32) return CUDNN_FMA_MATH;
+    if (cfg.precision == DP_PREC_TF32) return CUDNN_DEFAULT_MATH;   // fp32 data -> TF32 tensor cores
+    return CUDNN_TENSOR_OP_MATH;
+  }
+  void make_gn(GNW& g_, int C) {
+    g_.C = C;
+    g_.gamma = (float*)dmalloc((size_t)C * 4);
+    g_.beta = (float*)dmalloc((size_t)C * 4);
+  }
+
+  void allocate() {
+    const size_t n = (size_t)chunk;
+    make_conv(stem, 3, STEM_CH, 7, 2, 3, Cp);
+    for (auto& b : blocks) {
+      make_gn(b.n1, b.cin); make_gn(b.n2, b.mid); make_gn(b.n3, b.mid);
+      if (b.has_ds) make_conv(b.ds, b.cin, b.cout, 1, b.stride, 0, b.cin);
+      make_conv(b.c1, b.cin, b.mid, 1, 1, 0, b.cin);
+      make_conv(b.c2, b.mid, b.mid, 3, b.stride, 1, b.mid);
+      make_conv(b.c3, b.mid, b.cout, 1, 1, 0, b.mid);
+      b.h1 = dmalloc(n * b.hin * b.hin * b.mid * es);
+      b.h2 = dmalloc(n * b.hout * b.hout * b.mid * es);
+      b.out = dmalloc(n * b.hout * b.hout * b.cout * es);
+      b.st1 = (float*)dmalloc(n * dp::GN_GROUPS * 2 * 4);
+      b.st2 = (float*)dmalloc(n * dp::GN_GROUPS * 2 * 4);
+      b.st3 = (float*)dmalloc(n * dp::GN_GROUPS * 2 * 4);
+    }
+    make_gn(head_gn, WIDTHS[3]);
+    fc_w = (float*)dmalloc((size_t)K * WIDTHS[3] * 4);
+    fc_b = (float*)dmalloc((size_t)K * 4);
+    const size_t ma = max_act_elems();
+    net_in = dmalloc(n * H * H * Cp * es);
+    act = dmalloc(n * ma * es);
+    act2 = dmalloc(n * ma * es / 4 + 256);
+    x0 = dmalloc(n * Hp() * Hp() * STEM_CH * es);
+    pool_amax = (int8_t*)dmalloc(n * Hp() * Hp() * STEM_CH);
+    for (int i = 0; i < 4; ++i) g[i] = dmalloc(n * ma * es);
+    gn_partial = (float*)dmalloc(n * dp::GN_MAX_SPLITS * dp::GN_GROUPS * 2 * 4);
+    head_stats = (float*)dmalloc(n * dp::GN_GROUPS * 2 * 4);
+    pooled = (float*)dmalloc(n * WIDTHS[3] * 4);
+    dpooled = (float*)dmalloc(n * WIDTHS[3] * 4);
+    logits = (float*)dmalloc(n * K * 4);
+    dlogits = (float*)dmalloc(n * K * 4);
+    lib_ws_bytes = (size_t)512 << 20;
+    lib_ws = dmalloc(lib_ws_bytes);
+    const size_t B = (size_t)cfg.max_images, HW = (size_t)H * H;
+    adv_x = (float*)dmalloc(B * 3 * HW * 4);
+    dLs = (float*)dmalloc(B * 3 * HW * 4);
+    host_x = (float*)dmalloc(B * 3 * HW * 4);
+    host_pattern = (float*)dmalloc(B * 3 * HW * 4);
+    host_mask = (float*)dmalloc(B * HW * 4);
+    host_G = (float*)dmalloc(B * 3 * HW * 4);
+    for (float** p : {&scale, &l2, &loss_struc, &loss_density, &group_lasso, &lr_d, &structured_d, &coeff_d})
+      *p = (float*)dmalloc(B * 4);
+    win_dev = (float*)dmalloc(B * 64 * 4);
+    grp_ss = (float*)dmalloc(B * (H / UNIT) * (H / UNIT) * 4);
+    ensure_samples(chunk);
+    ensure_pin((size_t)4 << 20);
+  }
+
+  // ---- weights -------------------------------------------------------------------------
+  void upload_conv(ConvW& c, const float* host, int64_t numel, cudaStream_t st, float* tmp) {
+    const int64_t want = (int64_t)c.cout * c.cin * c.k * c.k;
+    if (numel != want) fail("conv weight numel %lld != expected %lld", (long long)numel, (long long)want);
+    CUDA_OK(cudaMemcpyAsync(tmp, host, (size_t)numel * 4, cudaMemcpyHostToDevice, st));
+    dp::launch_weight_standardize(tmp, c.w, c.cout, c.cin, c.k, c.k, c.cin_pad, bf16, true, st);
+    KERNEL_OK();
+    CUDA_OK(cudaStreamSynchronize(st));
+  }
+  void upload_vec(float* dst, const float* host, int64_t numel, int64_t want) {
+    if (numel != want) fail("vector numel %lld != expected %lld", (long long)numel, (long long)want);
+    CUDA_OK(cudaMemcpy(dst, host, (size_t)numel * 4, cudaMemcpyHostToDevice));
+  }
+  void load_weights(int n, const char* const* names, const float* const* ptrs, const int64_t* numels) {
+    std::map<std::string, int> idx;
+    for (int i = 0; i < n; ++i) idx[names[i]] = i;
+    auto get = [&](const std::string& k) -> int {
+      auto it = idx.find(k);
+      if (it == idx.end()) fail("missing weight tensor '%s'", k.c_str());
+      return it->second;
+    };
+    float* tmp = nullptr;
+    CUDA_OK(cudaMalloc((void**)&tmp, (size_t)2048 * 2048 * 9 * 4 / 4 + (size_t)K * 2048 * 4));
+    cudaStream_t st = 0;
+    try {
+      int i = get("stem.conv.weight");
+      upload_conv(stem, ptrs[i], numels[i], st, tmp);
+      int s = 0, bi = 0;
+      for (auto& b : blocks) {
+        char pre[64];
+        snprintf(pre, sizeof(pre), "stages.%d.blocks.%d.", s, bi);
+        auto P = [&](const char* suffix) { return std::string(pre) + suffix; };
+        if (b.has_ds) { i = get(P("downsample.conv.weight")); upload_conv(b.ds, ptrs[i], numels[i], st, tmp); }
+        i = get(P("conv1.weight")); upload_conv(b.c1, ptrs[i], numels[i], st, tmp);
+        i = get(P("conv2.weight")); upload_conv(b.c2, ptrs[i], numels[i], st, tmp);
+        i = get(P("conv3.weight")); upload_conv(b.c3, ptrs[i], numels[i], st, tmp);
+        i = get(P("norm1.weight")); upload_vec(b.n1.gamma, ptrs[i], numels[i], b.cin);
+        i = get(P("norm1.bias")); upload_vec(b.n1.beta, ptrs[i], numels[i], b.cin);
+        i = get(P("norm2.weight")); upload_vec(b.n2.gamma, ptrs[i], numels[i], b.mid);
+        i = get(P("norm2.bias")); upload_vec(b.n2.beta, ptrs[i], numels[i], b.mid);
+        i = get(P("norm3.weight")); upload_vec(b.n3.gamma, ptrs[i], numels[i], b.mid);
+        i = get(P("norm3.bias")); upload_vec(b.n3.beta, ptrs[i], numels[i], b.mid);
+        if (++bi == DEPTHS[s]) { bi = 0; ++s; }
+      }
+      i = get("norm.weight"); upload_vec(head_gn.gamma, ptrs[i], numels[i], WIDTHS[3]);
+      i = get("norm.bias"); upload_vec(head_gn.beta, ptrs[i], numels[i], WIDTHS[3]);
+      i = get("head.fc.weight"); upload_vec(fc_w, ptrs[i], numels[i], (int64_t)K * WIDTHS[3]);
+      i = get("head.fc.bias"); upload_vec(fc_b, ptrs[i], numels[i], K);
+    } catch (...) {
+      cudaFree(tmp);
+      throw;
+    }
+    cudaFree(tmp);
+    weights_loaded = true;
+  }
+
+  // ---- cuDNN convolution -------------------------------------------------------------
+  CudnnPlan& conv_plan(int layer_id, const ConvW& c, int N, int hin, int hout) {
+    auto key = std::make_pair(layer_id, N);
+    auto it = cudnn_plans.find(key);
+    if (it != cudnn_plans.end()) return it->second;
+    CudnnPlan p;
+    CUDNN_OK(cudnnCreateTensorDescriptor(&p.xdesc));
+    CUDNN_OK(cudnnCreateTensorDescriptor(&p.ydesc));
+    CUDNN_OK(cudnnSetTensor4dDescriptor(p.xdesc, CUDNN_TENSOR_NHWC, cudnn_dt, N, c.cin_pad, hin, hin));
+    CUDNN_OK(cudnnSetTensor4dDescriptor(p.ydesc, CUDNN_TENSOR_NHWC, cudnn_dt, N, c.cout, hout, hout));
+    int on, oc, oh, ow;
+    CUDNN_OK(cudnnGetConvolution2dForwardOutputDim(c.cdesc, p.xdesc, c.wdesc, &on, &oc, &oh, &ow));
+    if (on != N || oc != c.cout || oh != hout || ow != hout)
+      fail("conv layer %d: cuDNN output dims (%d,%d,%d,%d) != expected (%d,%d,%d,%d)", layer_id, on, oc, oh, ow, N, c.cout, hout, hout);
+    return cudnn_plans.emplace(key, p).first->second;
+  }
+  bool math_ok(cudnnMathType_t m) const {
+    if (cfg.precision == DP_PREC_FP32) return m == CUDNN_FMA_MATH;   // parity mode: no TF32 down-conversion
+    return true;
+  }
+  void pick_fwd(CudnnPlan& p, const ConvW& c, const void* x, void* y) {
+    cudnnConvolutionFwdAlgoPerf_t perf[16];
+    int got = 0;
+    if (cfg.autotune)
+      CUDNN_OK(cudnnFindConvolutionForwardAlgorithmEx(cudnn, p.xdesc, x, c.wdesc, c.w, c.cdesc, p.ydesc, y, 16, &got, perf, lib_ws, lib_ws_bytes));
+    else
+      CUDNN_OK(cudnnGetConvolutionForwardAlgorithm_v7(cudnn, p.xdesc, c.wdesc, c.cdesc, p.ydesc, 16, &got, perf));
+    for (int i = 0; i < got; ++i) {
+      if (perf[i].status != CUDNN_STATUS_SUCCESS || perf[i].memory > lib_ws_bytes || !math_ok(perf[i].mathType)) continue;
+      p.fwd_algo = perf[i].algo; p.fwd_math = perf[i].mathType; p.fwd_ws = perf[i].memory; p.fwd_ready = true;
+      return;
+    }
+    fail("no usable cuDNN forward algorithm (cin=%d cout=%d k=%d stride=%d, %d candidates)", c.cin_pad, c.cout, c.k, c.stride, got);
+  }
+  void pick_bwd(CudnnPlan& p, const ConvW& c, const void* dy, void* dx) {
+    cudnnConvolutionBwdDataAlgoPerf_t perf[16];
+    int got = 0;
+    if (cfg.autotune)
+      CUDNN_OK(cudnnFindConvolutionBackwardDataAlgorithmEx(cudnn, c.wdesc, c.w, p.ydesc, dy, c.cdesc, p.xdesc, dx, 16, &got, perf, lib_ws, lib_ws_bytes));
+    else
+      CUDNN_OK(cudnnGetConvolutionBackwardDataAlgorithm_v7(cudnn, c.wdesc, p.ydesc, c.cdesc, p.xdesc, 16, &got, perf));
+    int fallback = -1;
+    for (int i = 0; i < got; ++i) {
+      if (perf[i].status != CUDNN_STATUS_SUCCESS || perf[i].memory > lib_ws_bytes || !math_ok(perf[i].mathType)) continue;
+      if (perf[i].determinism != CUDNN_DETERMINISTIC) { if (fallback < 0) fallback = i; continue; }
+      p.bwd_algo = perf[i].algo; p.bwd_math = perf[i].mathType; p.bwd_ws = perf[i].memory; p.bwd_ready = true;
+      return;
+    }
+    if (fallback >= 0) {
+      p.bwd_algo = perf[fallback].algo; p.bwd_math = perf[fallback].mathType; p.bwd_ws = perf[fallback].memory; p.bwd_ready = true;
+      return;
+    }
+    fail("no usable cuDNN backward-data algorithm (cin=%d cout=%d k=%d stride=%d, %d candidates)", c.cin_pad, c.cout, c.k, c.stride, got);
+  }
+  void conv_fwd(int layer_id, const ConvW& c, int N, int hin, int hout, const void* x, void* y, cudaStream_t st) {
+    CudnnPlan& p = conv_plan(layer_id, c, N, hin, hout);
+    if (!p.fwd_ready) pick_fwd(p, c, x, y);
+    CUDNN_OK(cudnnSetConvolutionMathType(c.cdesc, p.fwd_math));
+    const float one = 1.f, zero = 0.f;
+    CUDNN_OK(cudnnConvolutionForward(cudnn, &one, p.xdesc, x, c.wdesc, c.w, c.cdesc, p.fwd_algo, lib_ws, lib_ws_bytes, &zero, p.ydesc, y));
+    ++launches;
+  }
+  void conv_bwd(int layer_id, const ConvW& c, int N, int hin, int hout, const void* dy, void* dx, cudaStream_t st) {
+    CudnnPlan& p = conv_plan(layer_id, c, N, hin, hout);
+    if (!p.bwd_ready) pick_bwd(p, c, dy, dx);
+    CUDNN_OK(cudnnSetConvolutionMathType(c.cdesc, p.bwd_math));
+    const float one = 1.f, zero = 0.f;
+    CUDNN_OK(cudnnConvolutionBackwardData(cudnn, &one, c.wdesc, c.w, p.ydesc, dy, c.cdesc, p.bwd_algo, lib_ws, lib_ws_bytes, &zero, p.xdesc, dx));
+    ++launches;
+  }
+
+  // ---- cublasLt GEMM (1x1 convolutions, NHWC) ---------------------------------------------
+  // mode 0: Y[rows,nout] = X[rows,k] * W[nout,k]^T (+ Cres)      (forward)
+  // mode 1: dX[rows,nout] = dY[rows,k] * W[k,nout] (+ dX if beta) (backward data)
+  GemmPlan& gemm_plan(int rows, int nout, int k, int mode) {
+    auto key = std::make_tuple(rows, nout, k, mode);
+    auto it = gemm_plans.find(key);
+    if (it != gemm_plans.end()) return it->second;
+    GemmPlan p;
+    CUBLAS_OK(cublasLtMatmulDescCreate(&p.op, lt_compute, CUDA_R_32F));
+    const cublasOperation_t ta = (mode == 0) ? CUBLAS_OP_T : CUBLAS_OP_N, tb = CUBLAS_OP_N;
+    CUBLAS_OK(cublasLtMatmulDescSetAttribute(p.op, CUBLASLT_MATMUL_DESC_TRANSA, &ta, sizeof(ta)));
+    CUBLAS_OK(cublasLtMatmulDescSetAttribute(p.op, CUBLASLT_MATMUL_DESC_TRANSB, &tb, sizeof(tb)));
+    // column-major view: D[nout x rows] = op(A) * B
+    if (mode == 0) CUBLAS_OK(cublasLtMatrixLayoutCreate(&p.a, cuda_dt, k, nout, k));       // W as col-major [k x nout], ld k
+    else CUBLAS_OK(cublasLtMatrixLayoutCreate(&p.a, cuda_dt, nout, k, nout));              // W[k rows][nout] as col-major [nout x k], ld nout
+    CUBLAS_OK(cublasLtMatrixLayoutCreate(&p.b, cuda_dt, k, rows, k));                      // X / dY as col-major [k x rows]
+    CUBLAS_OK(cublasLtMatrixLayoutCreate(&p.c, cuda_dt, nout, rows, nout));
+    cublasLtMatmulPreference_t pref;
+    CUBLAS_OK(cublasLtMatmulPreferenceCreate(&pref));
+    CUBLAS_OK(cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES, &lib_ws_bytes, sizeof(lib_ws_bytes)));
+    cublasLtMatmulHeuristicResult_t res[4];
+    int got = 0;
+    cublasStatus_t s = cublasLtMatmulAlgoGetHeuristic(lt, p.op, p.a, p.b, p.c, p.c, pref, 4, res, &got);
+    cublasLtMatmulPreferenceDestroy(pref);
+    if (s != CUBLAS_STATUS_SUCCESS || got == 0) fail("cublasLt: no algorithm for GEMM rows=%d nout=%d k=%d mode=%d (status %d)", rows, nout, k, mode, (int)s);
+    p.algo = res[0].algo;
+    return gemm_plans.emplace(key, p).first->second;
+  }
+  void gemm(int rows, int nout, int k, int mode, const void* W, const void* X, const void* Cres, float beta, void* D, cudaStream_t st) {
+    GemmPlan& p = gemm_plan(rows, nout, k, mode);
+    const float one = 1.f;
+    CUBLAS_OK(cublasLtMatmul(lt, p.op, &one, W, p.a, X, p.b, &beta, Cres ? Cres : D, p.c, D, p.c, &p.algo, lib_ws, lib_ws_bytes, st));
+    ++launches;
+  }
+
+  // ---- classifier forward ------------------------------------------------------------------
+  // input: [N,H,H,Cp] T.  train: keep what backward needs.  Leaves logits in `logits`.
+  void forward(int N, const void* input, bool train, cudaStream_t st) {
+    if (!weights_loaded) fail("dp_engine_load_weights has not been called");
+    if (N > chunk) fail("forward: N=%d exceeds chunk=%d", N, chunk);
+    CUDNN_OK(cudnnSetStream(cudnn, st));
+    const int hs = Hs(), hp = Hp();
+    conv_fwd(0, stem, N, H, hs, input, act, st);
+    dp::launch_maxpool_forward(act, x0, train ? pool_amax : nullptr, N, hs, hs, STEM_CH, bf16, st); KERNEL_OK(); ++launches;
+    const void* cur = x0;
+    int lid = 1;
+    for (auto& b : blocks) {
+      const int pin_ = b.hin * b.hin, pout = b.hout * b.hout;
+      // xp = relu(gn1(cur))
+      dp::launch_gn_relu_forward(cur, act, b.n1.gamma, b.n1.beta, gn_partial, b.st1, N, pin_, b.cin, bf16, st); KERNEL_OK(); launches += 2;
+      const void* shortcut = cur;
+      if (b.has_ds) {
+        const void* src = act;
+        if (b.stride == 2) { dp::launch_subsample2(act, act2, N, b.hin, b.hin, b.cin, bf16, st); KERNEL_OK(); ++launches; src = act2; }
+        gemm(N * pout, b.cout, b.cin, 0, b.ds.w, src, nullptr, 0.f, b.out, st);
+        shortcut = b.out;
+      }
+      gemm(N * pin_, b.mid, b.cin, 0, b.c1.w, act, nullptr, 0.f, b.h1, st);
+      dp::launch_gn_relu_forward(b.h1, act, b.n2.gamma, b.n2.beta, gn_partial, b.st2, N, pin_, b.mid, bf16, st); KERNEL_OK(); launches += 2;
+      conv_fwd(lid, b.c2, N, b.hin, b.hout, act, b.h2, st);
+      dp::launch_gn_relu_forward(b.h2, act, b.n3.gamma, b.n3.beta, gn_partial, b.st3, N, pout, b.mid, bf16, st); KERNEL_OK(); launches += 2;
+      gemm(N * pout, b.cout, b.mid, 0, b.c3.w, act, shortcut, 1.f, b.out, st);   // + shortcut fused as C operand
+      cur = b.out;
+      ++lid;
+    }
+    const Block& last = blocks.back();
+    const int pl = last.hout * last.hout;
+    dp::launch_gn_stats(cur, gn_partial, head_stats, N, pl, last.cout, bf16, st); KERNEL_OK(); launches += 2;
+    dp::launch_head_pool(cur, head_gn.gamma, head_gn.beta, head_stats, pooled, N, pl, last.cout, bf16, st); KERNEL_OK(); ++launches;
+    dp::launch_fc_forward(pooled, fc_w, fc_b, logits, N, last.cout, K, st); KERNEL_OK(); ++launches;
+  }
+
+  // ---- classifier backward (to the input) -----------------------------------------------------
+  // dlog: [N,K] fp32 dev.  Leaves d/d(input) in `d_input` ([N,H,H,Cp] T).
+  void backward(int N, const float* dlog, cudaStream_t st) {
+    CUDNN_OK(cudnnSetStream(cudnn, st));
+    const Block& last = blocks.back();
+    const int pl = last.hout * last.hout;
+    void *GA = g[0], *GB = g[1], *GC = g[2], *GD = g[3];
+    dp::launch_fc_backward(dlog, fc_w, dpooled, N, last.cout, K, st); KERNEL_OK(); ++launches;
+    dp::launch_pool_grad_bcast(dpooled, GB, N, pl, last.cout, bf16, st); KERNEL_OK(); ++launches;
+    dp::launch_gn_relu_backward(GB, last.out, nullptr, GA, head_gn.gamma, head_gn.beta, head_stats, gn_partial, N, pl, last.cout, bf16, st); KERNEL_OK(); launches += 2;
+    for (int bi = (int)blocks.size() - 1; bi >= 0; --bi) {
+      Block& b = blocks[bi];
+      const int lid = bi + 1;
+      const int pin_ = b.hin * b.hin, pout = b.hout * b.hout;
+      const void* xin = (bi == 0) ? x0 : blocks[bi - 1].out;
+      // d_a3 = d_out * W3
+      gemm(N * pout, b.mid, b.cout, 1, b.c3.w, GA, nullptr, 0.f, GB, st);
+      dp::launch_gn_relu_backward(GB, b.h2, nullptr, GC, b.n3.gamma, b.n3.beta, b.st3, gn_partial, N, pout, b.mid, bf16, st); KERNEL_OK(); launches += 2;
+      conv_bwd(lid, b.c2, N, b.hin, b.hout, GC, GB, st);
+      dp::launch_gn_relu_backward(GB, b.h1, nullptr, GC, b.n2.gamma, b.n2.beta, b.st2, gn_partial, N, pin_, b.mid, bf16, st); KERNEL_OK(); launches += 2;
+      gemm(N * pin_, b.cin, b.mid, 1, b.c1.w, GC, nullptr, 0.f, GB, st);          // d_xp (conv1 path)
+      if (b.has_ds) {
+        if (b.stride == 2) {
+          gemm(N * pout, b.cin, b.cout, 1, b.ds.w, GA, nullptr, 0.f, GC, st);
+          dp::launch_subsample2_adjoint_add(GC, GB, N, b.hin, b.hin, b.cin, bf16, st); KERNEL_OK(); ++launches;
+        } else {
+          gemm(N * pout, b.cin, b.cout, 1, b.ds.w, GA, nullptr, 1.f, GB, st);    // accumulate
+        }
+        dp::launch_gn_relu_backward(GB, xin, nullptr, GD, b.n1.gamma, b.n1.beta, b.st1, gn_partial, N, pin_, b.cin, bf16, st); KERNEL_OK(); launches += 2;
+      } else {
+        dp::launch_gn_relu_backward(GB, xin, GA, GD, b.n1.gamma, b.n1.beta, b.st1, gn_partial, N, pin_, b.cin, bf16, st); KERNEL_OK(); launches += 2;
+      }
+      std::swap(GA, GD);
+    }
+    const int hs = Hs();
+    dp::launch_maxpool_backward(GA, pool_amax, GB, N, hs, hs, STEM_CH, bf16, st); KERNEL_OK(); ++launches;
+    conv_bwd(0, stem, N, H, hs, GB, GC, st);
+    d_input = GC;
+  }
+
+  // ---- helpers for the attack entry points --------------------------------------------------
+  void h2d_samples(const int16_t* rects_host, int N, cudaStream_t st) {
+    ensure_samples(N);
+    if (rects_host != nullptr) {
+      const size_t bytes = (size_t)N * 16 * sizeof(int16_t);
+      ensure_pin(bytes);
+      memcpy(pin, rects_host, bytes);
+      CUDA_OK(cudaMemcpyAsync(rects_d, pin, bytes, cudaMemcpyHostToDevice, st));
+      CUDA_OK(cudaStreamSynchronize(st));   // `pin` is reused right after
+    }
+  }
+  void check_B(int B) const {
+    if (B < 1 || B > cfg.max_images) fail("B=%d outside [1, max_images=%d]", B, cfg.max_images);
+  }
+};
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+#define DP_TRY try {
+#define DP_CATCH                                   \
+  }                                                \
+  catch (const std::exception& ex) {               \
+    g_last_error = ex.what();                      \
+    return 1;                                      \
+  }                                                \
+  catch (...) {                                    \
+    g_last_error = "unknown C++ exception";        \
+    return 1;                                      \
+  }                                                \
+  return 0;
+
+extern "C" {
+
+int32_t dp_abi_version(void) { return DP_ABI_VERSION; }
+const char* dp_last_error(void) { return g_last_error.c_str(); }
+
+int32_t dp_engine_create(const dp_config* cfg, dp_engine** out) {
+  DP_TRY
+  if (!cfg || !out) fail("null argument");
+  if (cfg->img % 56 != 0 || cfg->img < 56) fail("img=%d must be a positive multiple of 56", cfg->img);
+  if (cfg->chunk < 1) fail("chunk must be >= 1");
+  if (cfg->max_images < 1) fail("max_images must be >= 1");
+  if (cfg->precision < 0 || cfg->precision > 2) fail("unknown precision %d", cfg->precision);
+  int ndev = 0;
+  CUDA_OK(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) fail("device %d not present (%d CUDA devices)", cfg->device, ndev);
+  CUDA_OK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10) fail("device %d is sm_%d%d; this engine is built for sm_100a (B200) only", cfg->device, prop.major, prop.minor);
+  dp_engine* e = new dp_engine();
+  try {
+    e->cfg = *cfg;
+    e->num_sms = prop.multiProcessorCount;
+    e->bf16 = (cfg->precision == DP_PREC_BF16);
+    e->es = e->bf16 ? 2 : 4;
+    e->Cp = e->bf16 ? 8 : 4;
+    if (const char* s = getenv("DORPATCH_CPAD")) e->Cp = atoi(s);
+    if (e->Cp != 3 && e->Cp != 4 && e->Cp != 8) fail("DORPATCH_CPAD must be 3, 4 or 8");
+    e->H = cfg->img; e->K = cfg->n_classes; e->chunk = cfg->chunk;
+    e->cudnn_dt = e->bf16 ? CUDNN_DATA_BFLOAT16 : CUDNN_DATA_FLOAT;
+    e->cuda_dt = e->bf16 ? CUDA_R_16BF : CUDA_R_32F;
+    e->lt_compute = (cfg->precision == DP_PREC_TF32) ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F;
+    CUDNN_OK(cudnnCreate(&e->cudnn));
+    CUBLAS_OK(cublasLtCreate(&e->lt));
+    e->build_arch();
+    e->allocate();
+  } catch (...) {
+    dp_engine_destroy(e);
+    throw;
+  }
+  *out = e;
+  DP_CATCH
+}
+
+void dp_engine_destroy(dp_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto& kv : e->cudnn_plans) {
+    if (kv.second.xdesc) cudnnDestroyTensorDescriptor(kv.second.xdesc);
+    if (kv.second.ydesc) cudnnDestroyTensorDescriptor(kv.second.ydesc);
+  }
+  for (auto& kv : e->gemm_plans) {
+    cublasLtMatmulDescDestroy(kv.second.op);
+    cublasLtMatrixLayoutDestroy(kv.second.a);
+    cublasLtMatrixLayoutDestroy(kv.second.b);
+    cublasLtMatrixLayoutDestroy(kv.second.c);
+  }
+  auto kill = [](ConvW& c) {
+    if (c.wdesc) cudnnDestroyFilterDescriptor(c.wdesc);
+    if (c.cdesc) cudnnDestroyConvolutionDescriptor(c.cdesc);
+  };
+  kill(e->stem);
+  for (auto& b : e->blocks) { kill(b.ds); kill(b.c1); kill(b.c2); kill(b.c3); }
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->pin) cudaFreeHost(e->pin);
+  if (e->cudnn) cudnnDestroy(e->cudnn);
+  if (e->lt) cublasLtDestroy(e->lt);
+  delete e;
+}
+
+int32_t dp_engine_load_weights(dp_engine* e, int32_t n, const char* const* names, const float* const* ptrs, const int64_t* numels) {
+  DP_TRY
+  if (!e) fail("null engine");
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  e->load_weights(n, names, ptrs, numels);
+  DP_CATCH
+}
+
+int64_t dp_engine_device_bytes(const dp_engine* e) { return e ? e->device_bytes : 0; }
+int64_t dp_engine_launch_count(const dp_engine* e) { return e ? e->launches : 0; }
+
+int32_t dp_input_layout(const dp_engine* e, int32_t* c_pad, int32_t* elem_bytes) {
+  DP_TRY
+  if (!e) fail("null engine");
+  if (c_pad) *c_pad = e->Cp;
+  if (elem_bytes) *elem_bytes = (int32_t)e->es;
+  DP_CATCH
+}
+
+int32_t dp_paste(dp_engine* e, const float* x, const float* mask, const float* pattern, int32_t B, float eps,
+                 float* adv_x_out, float* l2_host, float* scale_host, void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  e->check_B(B);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  dp::launch_paste(x, mask, pattern, adv_x_out ? adv_x_out : e->adv_x, e->l2, e->scale, B, e->H, e->H, eps, st); KERNEL_OK(); ++e->launches;
+  if (l2_host) CUDA_OK(cudaMemcpyAsync(l2_host, e->l2, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (scale_host) CUDA_OK(cudaMemcpyAsync(scale_host, e->scale, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (l2_host || scale_host) CUDA_OK(cudaStreamSynchronize(st));
+  DP_CATCH
+}
+
+int32_t dp_window_sum(dp_engine* e, const float* t, int32_t B, int32_t k, int32_t square, float* out_host, void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  e->check_B(B);
+  if (k < 1 || e->H % k != 0) fail("window %d does not divide img %d", k, e->H);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  const size_t n = (size_t)B * (e->H / k) * (e->H / k);
+  float* tmp = e->dLs;   // scratch: at most B*H*W floats
+  dp::launch_window_sum(t, tmp, B, e->H, e->H, k, square != 0, st); KERNEL_OK(); ++e->launches;
+  CUDA_OK(cudaMemcpyAsync(out_host, tmp, n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  DP_CATCH
+}
+
+int32_t dp_expand(dp_engine* e, const float* img, int32_t B, int32_t S, const int16_t* rects_host, void* out, void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  const int N = B * S;
+  if (out == nullptr && N > e->chunk) fail("dp_expand: B*S=%d exceeds chunk=%d and no output buffer was given", N, e->chunk);
+  e->h2d_samples(rects_host, N, st);
+  dp::launch_expand(img, nullptr, nullptr, nullptr, nullptr, rects_host ? e->rects_d : nullptr, out ? out : e->net_in,
+                    B, S, 0, N, e->H, e->H, e->Cp, e->bf16, false, e->num_sms, st);
+  KERNEL_OK(); ++e->launches;
+  DP_CATCH
+}
+
+int32_t dp_predict(dp_engine* e, const float* img, int32_t B, int32_t S, const int16_t* rects_host, int32_t* preds_host,
+                   float* logits_host, void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  const int N = B * S;
+  if (N < 1) fail("dp_predict: empty batch");
+  e->h2d_samples(rects_host, N, st);
+  for (int n0 = 0; n0 < N; n0 += e->chunk) {
+    const int n = std::min(e->chunk, N - n0);
+    dp::launch_expand(img, nullptr, nullptr, nullptr, nullptr, rects_host ? e->rects_d : nullptr, e->net_in, B, S, n0, n,
+                      e->H, e->H, e->Cp, e->bf16, false, e->num_sms, st);
+    KERNEL_OK(); ++e->launches;
+    e->forward(n, e->net_in, false, st);
+    dp::launch_argmax(e->logits, e->preds_d + n0, n, e->K, st); KERNEL_OK(); ++e->launches;
+    if (logits_host) CUDA_OK(cudaMemcpyAsync(logits_host + (size_t)n0 * e->K, e->logits, (size_t)n * e->K * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_OK(cudaMemcpyAsync(preds_host, e->preds_d, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  DP_CATCH
+}
+
+static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t st) {
+  if (!a) fail("null args");
+  e->check_B(a->B);
+  if (a->S < 1 || a->S_total < a->S) fail("bad S=%d / S_total=%d", a->S, a->S_total);
+  if (!a->x || !a->mask || !a->pattern || !a->grad_adv || !a->y_host || !a->targeted_host) fail("null pointer in dp_attack_args");
+  const int B = a->B, S = a->S, N = B * S, H = e->H;
+  e->ensure_samples(N);
+  // per-sample labels / criterion flags / rectangles -> device.  Pinned staging layout:
+  // [H2D region: ys | tg | rects][D2H region: results]; the regions never overlap.
+  const size_t rect_bytes = a->rects_host ? (size_t)N * 16 * sizeof(int16_t) : 0;
+  const size_t h2d_bytes = (((size_t)N * 5 + 15) / 16) * 16 + rect_bytes;
+  const size_t d2h_off = (h2d_bytes + 255) / 256 * 256;
+  e->ensure_pin(d2h_off + (size_t)N * 8 + (size_t)B * 16 + 512);
+  int32_t* ys = (int32_t*)e->pin;
+  uint8_t* tg = (uint8_t*)(ys + N);
+  unsigned char* rp = (unsigned char*)e->pin + (((size_t)N * 5 + 15) / 16) * 16;
+  for (int b = 0; b < B; ++b)
+    if (a->y_host[b] < 0 || a->y_host[b] >= e->K) fail("label %lld of image %d outside [0,%d)", (long long)a->y_host[b], b, e->K);
+  for (int b = 0; b < B; ++b)
+    for (int s = 0; s < S; ++s) { ys[b * S + s] = (int32_t)a->y_host[b]; tg[b * S + s] = a->targeted_host[b]; }
+  if (rect_bytes) memcpy(rp, a->rects_host, rect_bytes);
+  CUDA_OK(cudaMemcpyAsync(e->y_d, ys, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->tg_d, tg, (size_t)N, cudaMemcpyHostToDevice, st));
+  if (rect_bytes) CUDA_OK(cudaMemcpyAsync(e->rects_d, rp, rect_bytes, cudaMemcpyHostToDevice, st));
+  const int16_t* rects = rect_bytes ? e->rects_d : nullptr;
+
+  dp::launch_paste(a->x, a->mask, a->pattern, e->adv_x, e->l2, e->scale, B, H, H, a->eps, st); KERNEL_OK(); ++e->launches;
+  dp::launch_struct(e->adv_x, a->x, e->loss_struc, e->dLs, B, H, H, st); KERNEL_OK(); ++e->launches;
+  if (a->stage == 0) {
+    dp::launch_maskreg(a->mask, e->loss_density, e->group_lasso, e->win_dev, e->grp_ss, B, H, H, UNIT, st); KERNEL_OK(); ++e->launches;
+  }
+  const float inv_s = 1.0f / (float)a->S_total;
+  for (int n0 = 0; n0 < N; n0 += e->chunk) {
+    const int n = std::min(e->chunk, N - n0);
+    dp::launch_expand(nullptr, a->x, a->mask, a->pattern, e->scale, rects, e->net_in, B, S, n0, n, H, H, e->Cp, e->bf16, true, e->num_sms, st);
+    KERNEL_OK(); ++e->launches;
+    e->forward(n, e->net_in, true, st);
+    dp::launch_cw(e->logits, e->y_d + n0, e->tg_d + n0, a->confidence, inv_s, e->loss_d + n0, e->preds_d + n0, e->dlogits, n, e->K, st);
+    KERNEL_OK(); ++e->launches;
+    e->backward(n, e->dlogits, st);
+    dp::launch_reduce(e->d_input, rects, a->grad_adv, B, S, n0, n, H, H, e->Cp, e->bf16, st); KERNEL_OK(); ++e->launches;
+  }
+  // results -> host (pinned staging, one sync)
+  unsigned char* out = e->pin + d2h_off;
+  size_t off = 0;
+  auto d2h = [&](const void* src, size_t bytes) { void* dst = out + off; CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st)); off += (bytes + 15) / 16 * 16; return dst; };
+  void* p_loss = d2h(e->loss_d, (size_t)N * 4);
+  void* p_pred = d2h(e->preds_d, (size_t)N * 4);
+  void* p_ls = d2h(e->loss_struc, (size_t)B * 4);
+  void* p_ld = d2h(e->loss_density, (size_t)B * 4);
+  void* p_gl = d2h(e->group_lasso, (size_t)B * 4);
+  void* p_l2 = d2h(e->l2, (size_t)B * 4);
+  CUDA_OK(cudaStreamSynchronize(st));
+  if (a->loss_adv_host) memcpy(a->loss_adv_host, p_loss, (size_t)N * 4);
+  if (a->preds_host) memcpy(a->preds_host, p_pred, (size_t)N * 4);
+  if (a->loss_struc_host) memcpy(a->loss_struc_host, p_ls, (size_t)B * 4);
+  if (a->stage == 0 && a->loss_density_host) memcpy(a->loss_density_host, p_ld, (size_t)B * 4);
+  if (a->stage == 0 && a->group_lasso_host) memcpy(a->group_lasso_host, p_gl, (size_t)B * 4);
+  if (a->l2_host) memcpy(a->l2_host, p_l2, (size_t)B * 4);
+}
+
+static void attack_update_impl(dp_engine* e, const dp_update_args* u, cudaStream_t st) {
+  if (!u) fail("null args");
+  e->check_B(u->B);
+  if (!u->x || !u->mask || !u->pattern || !u->grad_adv || !u->lr_host || !u->structured_host) fail("null pointer in dp_update_args");
+  if (u->stage == 0 && !u->coeff_gl_host) fail("coeff_gl_host is required in stage 0");
+  const int B = u->B;
+  e->ensure_pin((size_t)B * 12 + 64);
+  float* h = (float*)e->pin;
+  for (int b = 0; b < B; ++b) { h[b] = u->lr_host[b]; h[B + b] = u->structured_host[b]; h[2 * B + b] = u->coeff_gl_host ? u->coeff_gl_host[b] : 0.f; }
+  CUDA_OK(cudaMemcpyAsync(e->lr_d, h, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->structured_d, h + B, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->coeff_d, h + 2 * B, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  dp::launch_update(u->x, u->mask, u->pattern, u->grad_adv, e->dLs, e->scale, e->win_dev, e->grp_ss, e->lr_d, e->structured_d,
+                    e->coeff_d, u->density, u->clip_min, u->clip_max, u->stage, u->grad_pattern_out, u->grad_mask_out, B, e->H, e->H, UNIT, st);
+  KERNEL_OK(); ++e->launches;
+  CUDA_OK(cudaStreamSynchronize(st));   // `pin` may be reused by the next call
+}
+
+int32_t dp_attack_grad(dp_engine* e, const dp_attack_args* a, void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  attack_grad_impl(e, a, (cudaStream_t)stream);
+  DP_CATCH
+}
+
+int32_t dp_attack_update(dp_engine* e, const dp_update_args* u, void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  attack_update_impl(e, u, (cudaStream_t)stream);
+  DP_CATCH
+}
+
+int32_t dp_attack_step_host(dp_engine* e, const dp_attack_args* g, const dp_update_args* u, void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  if (!g || !u) fail("null args");
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  e->check_B(g->B);
+  const size_t B = (size_t)g->B, HW = (size_t)e->H * e->H;
+  CUDA_OK(cudaMemcpyAsync(e->host_x, g->x, B * 3 * HW * 4, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->host_mask, g->mask, B * HW * 4, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->host_pattern, g->pattern, B * 3 * HW * 4, cudaMemcpyHostToDevice, st));
+  dp_attack_args ga = *g;
+  ga.x = e->host_x; ga.mask = e->host_mask; ga.pattern = e->host_pattern; ga.grad_adv = e->host_G;
+  attack_grad_impl(e, &ga, st);
+  dp_update_args ua = *u;
+  ua.x = e->host_x; ua.mask = e->host_mask; ua.pattern = e->host_pattern; ua.grad_adv = e->host_G;
+  ua.grad_pattern_out = nullptr; ua.grad_mask_out = nullptr;
+  attack_update_impl(e, &ua, st);
+  CUDA_OK(cudaMemcpyAsync(u->mask, e->host_mask, B * HW * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(u->pattern, e->host_pattern, B * 3 * HW * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  DP_CATCH
+}
+
+int32_t dp_net_forward_backward(dp_engine* e, const float* z, int32_t N, float* logits_dev, const float* dlogits_dev,
+                                float* dz_dev, void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N < 1 || N > e->chunk) fail("N=%d outside [1, chunk=%d]", N, e->chunk);
+  dp::launch_pack_nchw(z, e->net_in, N, e->H, e->H, e->Cp, e->bf16, st); KERNEL_OK(); ++e->launches;
+  e->forward(N, e->net_in, dlogits_dev != nullptr, st);
+  if (logits_dev) CUDA_OK(cudaMemcpyAsync(logits_dev, e->logits, (size_t)N * e->K * 4, cudaMemcpyDeviceToDevice, st));
+  if (dlogits_dev) {
+    if (!dz_dev) fail("dz_dev is required when dlogits_dev is given");
+    e->backward(N, dlogits_dev, st);
+    dp::launch_unpack_nhwc(e->d_input, dz_dev, N, e->H, e->H, e->Cp, e->bf16, st); KERNEL_OK(); ++e->launches;
+  }
+  DP_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// kernels.h -- host-side launchers of the hand-written sm_100a kernels.
+// Activation tensors are NHWC ("[N, P=H*W, C]"), element type fp32 or bf16 (`bf16` flag).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dp {
+
+constexpr int GN_GROUPS = 32;
+constexpr int GN_MAX_SPLITS = 16;
+
+// ---- classifier-side kernels (kernels_net.cu) --------------------------------------
+// timm StdConv2d standardisation of OIHW fp32 weights -> KRSC (NHWC filter), channel-padded.
+void launch_weight_standardize(const float* w_oihw, void* w_krsc, int O, int I, int kh, int kw, int Ipad,
+                               bool bf16, bool standardize, cudaStream_t st);
+// z [N,3,H,W] fp32 -> [N,H,W,Cp] T (pad channels zero) and back (first 3 channels).
+void launch_pack_nchw(const float* z, void* out, int N, int H, int W, int Cp, bool bf16, cudaStream_t st);
+void launch_unpack_nhwc(const void* in, float* dz, int N, int H, int W, int Cp, bool bf16, cudaStream_t st);
+
+int gn_splits(int P, int C, bool bf16);
+// GroupNorm(32)+ReLU forward: stats partials -> apply.  `stats` [N][32][2] receives (mean, rstd).
+void launch_gn_relu_forward(const void* x, void* y, const float* gamma, const float* beta, float* partial,
+                            float* stats, int N, int P, int C, bool bf16, cudaStream_t st);
+// statistics only (head): fills `stats`.
+void launch_gn_stats(const void* x, float* partial, float* stats, int N, int P, int C, bool bf16, cudaStream_t st);
+// backward of GroupNorm+ReLU wrt its input: dx = GNbwd(dy * relu'(.)) (+ addend).
+void launch_gn_relu_backward(const void* dy, const void* x, const void* addend, void* dx, const float* gamma,
+                             const float* beta, const float* stats, float* partial, int N, int P, int C, bool bf16,
+                             cudaStream_t st);
+// ConstantPad2d(1,0)+MaxPool(3,2): x [N,Hs,Ws,C] -> y [N,Hs/2,Ws/2,C]; argmax (int8, 0..8) optional.
+void launch_maxpool_forward(const void* x, void* y, int8_t* amax, int N, int Hs, int Ws, int C, bool bf16,
+                            cudaStream_t st);
+void launch_maxpool_backward(const void* dy, const int8_t* amax, void* dx, int N, int Hs, int Ws, int C, bool bf16,
+                             cudaStream_t st);
+// head: pooled[n][c] = mean_p relu(gn(x)); logits = pooled @ Wfc^T + b
+void launch_head_pool(const void* x, const float* gamma, const float* beta, const float* stats, float* pooled,
+                      int N, int P, int C, bool bf16, cudaStream_t st);
+void launch_fc_forward(const float* pooled, const float* w, const float* b, float* logits, int N, int C, int K,
+                       cudaStream_t st);
+void launch_fc_backward(const float* dlogits, const float* w, float* dpooled, int N, int C, int K, cudaStream_t st);
+// dy[n,p,c] = dpooled[n][c] / P
+void launch_pool_grad_bcast(const float* dpooled, void* dy, int N, int P, int C, bool bf16, cudaStream_t st);
+// strided spatial subsample [N,H,W,C] -> [N,H/2,W/2,C] (rows/cols 0,2,4,..) and its scatter-add adjoint
+void launch_subsample2(const void* x, void* y, int N, int H, int W, int C, bool bf16, cudaStream_t st);
+void launch_subsample2_adjoint_add(const void* dy, void* dx, int N, int H, int W, int C, bool bf16, cudaStream_t st);
+
+// ---- patch-side kernels (kernels_patch.cu) -------------------------------------------
+// utils.clip + add: adv_x = x + min(eps/||m(p-x)||,1) * m(p-x); l2[b], scale[b] dev outputs.
+void launch_paste(const float* x, const float* mask, const float* pattern, float* adv_x, float* l2, float* scale,
+                  int B, int H, int W, float eps, cudaStream_t st);
+// K1: EOT expansion (paste + normalise + occlude) -> [N,H,W,Cp] T.
+// fused==true: reads x/mask/pattern/scale (img ignored); else reads img [B,3,H,W].
+// rects [B*S][4][4] int16 dev or nullptr; samples [n0, n0+n) of the b-major ordering are
+// written to out + (n - n0) * H*W*Cp.
+void launch_expand(const float* img, const float* x, const float* mask, const float* pattern, const float* scale,
+                   const int16_t* rects, void* out, int B, int S, int n0, int n, int H, int W, int Cp, bool bf16,
+                   bool fused, int num_sms, cudaStream_t st);
+// K4: CW loss, argmax, dlogits (scaled by inv_s_total).  y/targeted are per-sample dev arrays.
+void launch_cw(const float* logits, const int32_t* y, const uint8_t* targeted, float confidence, float inv_s_total,
+               float* loss, int32_t* preds, float* dlogits, int N, int K, cudaStream_t st);
+void launch_argmax(const float* logits, int32_t* preds, int N, int K, cudaStream_t st);
+// K1^T: G[b] (+)= 2 * sum_s keep_s * dz[b,s]  for samples [n0,n0+n).
+void launch_reduce(const void* dz, const int16_t* rects, float* G, int B, int S, int n0, int n, int H, int W,
+                   int Cp, bool bf16, cudaStream_t st);
+// structural loss value [B] + gradient field dLs [B,3,H,W]  (attack.py:33-45,227-228)
+void launch_struct(const float* adv_x, const float* x, float* loss_struc, float* dLs, int B, int H, int W,
+                   cudaStream_t st);
+// density / group-lasso values + per-group statistics for their gradients (attack.py:72-80,235-245)
+void launch_maskreg(const float* mask, float* loss_density, float* group_lasso, float* win_dev, float* grp_ss,
+                    int B, int H, int W, int unit, cudaStream_t st);
+// K3: chain rule + sign step + clip (attack.py:332-342)
+void launch_update(const float* x, float* mask, float* pattern, const float* G, const float* dLs,
+                   const float* scale, const float* win_dev, const float* grp_ss, const float* lr,
+                   const float* structured, const float* coeff_gl, float density, float lo, float hi, int stage,
+                   float* gp_out, float* gm_out, int B, int H, int W, int unit, cudaStream_t st);
+// k x k window sums of [B,1,H,W] (optionally of the squares)
+void launch_window_sum(const float* t, float* out, int B, int H, int W, int k, bool square, cudaStream_t st);
+
+}  // namespace dp

@@ -1,0 +1,590 @@
+// kernels_net.cu -- hand-written sm_100a kernels around the classifier's tensor-core
+// convolutions: weight standardisation, GroupNorm(32)+ReLU forward / backward-to-input,
+// pad+maxpool, head (GN+ReLU+avgpool, fc), layout packers.  All activations NHWC.
+//
+// Restates the third-party classifier the reference uses (timm 0.6.7
+// resnetv2_50x1_bit_distilled, /root/reference/utils.py:51-58): StdConv2d eps=1e-8,
+// GroupNormAct(32 groups, eps=1e-5, ReLU), stem 'fixed' (ConstantPad2d(1,0)+MaxPool 3x3/2).
+// These kernels are HBM-bound; every one is a coalesced 16-byte-vector pass.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dp {
+
+#define DISPATCH_T(bf16, ...)                         \
+  do {                                                \
+    if (bf16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { using T = float; __VA_ARGS__; }            \
+  } while (0)
+
+// ------------------------------------------------------------------------------------
+// weight standardisation: one CTA per output channel
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void ws_kernel(const float* __restrict__ w, T* __restrict__ out, int I, int kh, int kw, int Ipad,
+                          int standardize) {
+  __shared__ float red[32];
+  const int o = blockIdx.x, n = I * kh * kw;
+  const float* wo = w + (size_t)o * n;
+  float mean = 0.f, rstd = 1.f;
+  if (standardize) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += wo[i];
+    mean = block_sum(s, red) / n;
+    float v = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { float d = wo[i] - mean; v += d * d; }
+    const float var = block_sum(v, red) / n;   // biased, as F.batch_norm(training=True)
+    rstd = 1.0f / sqrtf(var + 1e-8f);
+  }
+  T* oo = out + (size_t)o * kh * kw * Ipad;
+  for (int i = threadIdx.x; i < kh * kw * Ipad; i += blockDim.x) {
+    const int c = i % Ipad, rs = i / Ipad;
+    float v = 0.f;
+    if (c < I) v = (wo[(size_t)c * kh * kw + rs] - mean) * rstd;
+    oo[i] = from_float<T>(v);
+  }
+}
+
+void launch_weight_standardize(const float* w, void* out, int O, int I, int kh, int kw, int Ipad, bool bf16,
+                               bool standardize, cudaStream_t st) {
+  DISPATCH_T(bf16, (ws_kernel<T><<<O, 256, 0, st>>>(w, (T*)out, I, kh, kw, Ipad, standardize ? 1 : 0)));
+}
+
+// ------------------------------------------------------------------------------------
+// NCHW fp32 <-> NHWC(Cp) T
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_kernel(const float* __restrict__ z, T* __restrict__ out, int HW, int Cp, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t n = i / HW, p = i % HW;
+  for (int c = 0; c < Cp; ++c) {
+    float v = c < 3 ? z[(n * 3 + c) * HW + p] : 0.f;
+    out[i * Cp + c] = from_float<T>(v);
+  }
+}
+template <typename T>
+__global__ void unpack_kernel(const T* __restrict__ in, float* __restrict__ dz, int HW, int Cp, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t n = i / HW, p = i % HW;
+  for (int c = 0; c < 3; ++c) dz[(n * 3 + c) * HW + p] = to_float(in[i * Cp + c]);
+}
+void launch_pack_nchw(const float* z, void* out, int N, int H, int W, int Cp, bool bf16, cudaStream_t st) {
+  size_t total = (size_t)N * H * W;
+  DISPATCH_T(bf16, (pack_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(z, (T*)out, H * W, Cp, total)));
+}
+void launch_unpack_nhwc(const void* in, float* dz, int N, int H, int W, int Cp, bool bf16, cudaStream_t st) {
+  size_t total = (size_t)N * H * W;
+  DISPATCH_T(bf16, (unpack_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const T*)in, dz, H * W, Cp, total)));
+}
+
+// ------------------------------------------------------------------------------------
+// GroupNorm machinery.
+// A CTA of GN_THREADS threads walks a contiguous pixel slab of ONE sample.  Thread t owns
+// vector column (t % cols) [cols = C/V 16-byte vectors per pixel] and pixel rows
+// t/cols, t/cols + rpi, ...   When cols > GN_THREADS a thread owns several columns.
+// Partial group sums are combined in a fixed order (deterministic, no float atomics).
+// ------------------------------------------------------------------------------------
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAXCOLS_PER_THREAD = 2;   // C/V <= 512
+
+int gn_splits(int P, int C, bool bf16) {
+  const int V = bf16 ? 8 : 4;
+  const int cols = C / V;
+  const int rpi = cols >= GN_THREADS ? 1 : GN_THREADS / cols;   // pixel rows per iteration
+  int s = P / (rpi * 4);                                        // >= 4 iterations per CTA
+  if (s < 1) s = 1;
+  if (s > GN_MAX_SPLITS) s = GN_MAX_SPLITS;
+  return s;
+}
+
+// Per-thread accumulation of two per-channel quantities over the thread's pixels, then a
+// deterministic CTA reduction to per-group sums.  F(px, vals_x[V], c0, acc_a[V], acc_b[V]).
+template <typename T, typename F>
+__device__ __forceinline__ void gn_reduce_slab(int P, int C, int split, int splits, float* __restrict__ out_partial,
+                                               F&& body) {
+  constexpr int V = Vec<T>::N;
+  __shared__ float sm_a[GN_THREADS * V];
+  __shared__ float sm_b[GN_THREADS * V];
+  __shared__ float ch_a[2048];   // C <= 2048
+  __shared__ float ch_b[2048];
+  const int cols = C / V;
+  const int p0 = (int)(((long long)P * split) / splits), p1 = (int)(((long long)P * (split + 1)) / splits);
+  const int ncolblk = (cols + GN_THREADS - 1) / GN_THREADS;      // 1 or 2
+  const int cpt = cols < GN_THREADS ? cols : GN_THREADS;         // columns covered per pass
+  const int rpi = GN_THREADS / cpt;
+  const int tcol = threadIdx.x % cpt, trow = threadIdx.x / cpt;
+  for (int cb = 0; cb < ncolblk; ++cb) {
+    const int col = cb * GN_THREADS + tcol;
+    float a[V], b[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { a[i] = 0.f; b[i] = 0.f; }
+    if (col < cols)
+      for (int p = p0 + trow; p < p1; p += rpi) body(p, col * V, a, b);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { sm_a[threadIdx.x * V + i] = a[i]; sm_b[threadIdx.x * V + i] = b[i]; }
+    __syncthreads();
+    // channel totals: fixed-order sum over the rpi row-threads
+    for (int ch = threadIdx.x; ch < cpt * V; ch += GN_THREADS) {
+      const int c_col = ch / V, c_i = ch % V;
+      float ta = 0.f, tb = 0.f;
+      for (int r = 0; r < rpi; ++r) { ta += sm_a[(r * cpt + c_col) * V + c_i]; tb += sm_b[(r * cpt + c_col) * V + c_i]; }
+      const int gch = cb * GN_THREADS * V + ch;
+      if (gch < C) { ch_a[gch] = ta; ch_b[gch] = tb; }
+    }
+    __syncthreads();
+  }
+  const int cpg = C / GN_GROUPS;
+  if (threadIdx.x < GN_GROUPS) {
+    float ta = 0.f, tb = 0.f;
+    for (int i = 0; i < cpg; ++i) { ta += ch_a[threadIdx.x * cpg + i]; tb += ch_b[threadIdx.x * cpg + i]; }
+    out_partial[(split * GN_GROUPS + threadIdx.x) * 2 + 0] = ta;
+    out_partial[(split * GN_GROUPS + threadIdx.x) * 2 + 1] = tb;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const T* __restrict__ x, float* __restrict__ partial,
+                                                               int P, int C, int splits) {
+  constexpr int V = Vec<T>::N;
+  const int n = blockIdx.y, split = blockIdx.x;
+  const T* xn = x + (size_t)n * P * C;
+  gn_reduce_slab<T>(P, C, split, splits, partial + (size_t)n * splits * GN_GROUPS * 2,
+                    [&](int p, int c0, float* a, float* b) {
+                      Vec<T> v; v.load(xn + (size_t)p * C + c0);
+                      float f[V]; v.unpack(f);
+#pragma unroll
+                      for (int i = 0; i < V; ++i) { a[i] += f[i]; b[i] += f[i] * f[i]; }
+                    });
+}
+
+// finalise (mean, rstd) of sample n into shared memory from the split partials
+__device__ __forceinline__ void gn_finalize(const float* __restrict__ partial_n, int splits, float count,
+                                            float* s_mean, float* s_rstd) {
+  if (threadIdx.x < GN_GROUPS) {
+    float s = 0.f, q = 0.f;
+    for (int k = 0; k < splits; ++k) {
+      s += partial_n[(k * GN_GROUPS + threadIdx.x) * 2 + 0];
+      q += partial_n[(k * GN_GROUPS + threadIdx.x) * 2 + 1];
+    }
+    const float mean = s / count;
+    float var = q / count - mean * mean;
+    var = var < 0.f ? 0.f : var;
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rsqrtf(var + 1e-5f);
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int P, int C,
+                                   int splits) {
+  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+  const int n = blockIdx.x;
+  gn_finalize(partial + (size_t)n * splits * GN_GROUPS * 2, splits, (float)P * (C / GN_GROUPS), s_mean, s_rstd);
+  if (threadIdx.x < GN_GROUPS) {
+    stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 0] = s_mean[threadIdx.x];
+    stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 1] = s_rstd[threadIdx.x];
+  }
+}
+
+// y = relu(a*x + b), a = rstd*gamma, b = beta - mean*a.  grid (slabs, N).
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta,
+                                                               const float* __restrict__ partial,
+                                                               float* __restrict__ stats, int P, int C, int splits) {
+  constexpr int V = Vec<T>::N;
+  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+  const int n = blockIdx.y;
+  gn_finalize(partial + (size_t)n * splits * GN_GROUPS * 2, splits, (float)P * (C / GN_GROUPS), s_mean, s_rstd);
+  if (blockIdx.x == 0 && threadIdx.x < GN_GROUPS) {
+    stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 0] = s_mean[threadIdx.x];
+    stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 1] = s_rstd[threadIdx.x];
+  }
+  const int cols = C / V, cpg = C / GN_GROUPS;
+  const int p0 = (int)(((long long)P * blockIdx.x) / gridDim.x), p1 = (int)(((long long)P * (blockIdx.x + 1)) / gridDim.x);
+  const int cpt = cols < GN_THREADS ? cols : GN_THREADS, rpi = GN_THREADS / cpt;
+  const int tcol = threadIdx.x % cpt, trow = threadIdx.x / cpt;
+  const T* xn = x + (size_t)n * P * C;
+  T* yn = y + (size_t)n * P * C;
+  for (int col = tcol; col < cols; col += cpt) {
+    float a[V], b[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = col * V + i, g = c / cpg;
+      a[i] = s_rstd[g] * gamma[c];
+      b[i] = beta[c] - s_mean[g] * a[i];
+    }
+    for (int p = p0 + trow; p < p1; p += rpi) {
+      Vec<T> v; v.load(xn + (size_t)p * C + col * V);
+      float f[V]; v.unpack(f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) f[i] = fmaxf(fmaf(a[i], f[i], b[i]), 0.f);
+      v.pack(f); v.store(yn + (size_t)p * C + col * V);
+    }
+  }
+}
+
+static int apply_slabs(int P, int C, int V) {
+  const int cols = C / V;
+  const int cpt = cols < GN_THREADS ? cols : GN_THREADS, rpi = GN_THREADS / cpt;
+  int s = P / (rpi * 4);
+  if (s < 1) s = 1;
+  if (s > 32) s = 32;
+  return s;
+}
+
+void launch_gn_stats(const void* x, float* partial, float* stats, int N, int P, int C, bool bf16, cudaStream_t st) {
+  const int splits = gn_splits(P, C, bf16);
+  DISPATCH_T(bf16, (gn_stats_kernel<T><<<dim3(splits, N), GN_THREADS, 0, st>>>((const T*)x, partial, P, C, splits)));
+  DISPATCH_T(bf16, (gn_finalize_kernel<T><<<N, 32, 0, st>>>(partial, stats, P, C, splits)));
+}
+
+void launch_gn_relu_forward(const void* x, void* y, const float* gamma, const float* beta, float* partial,
+                            float* stats, int N, int P, int C, bool bf16, cudaStream_t st) {
+  const int splits = gn_splits(P, C, bf16);
+  DISPATCH_T(bf16, (gn_stats_kernel<T><<<dim3(splits, N), GN_THREADS, 0, st>>>((const T*)x, partial, P, C, splits)));
+  DISPATCH_T(bf16, (gn_apply_kernel<T><<<dim3(apply_slabs(P, C, Vec<T>::N), N), GN_THREADS, 0, st>>>(
+                       (const T*)x, (T*)y, gamma, beta, partial, stats, P, C, splits)));
+}
+
+// ---- backward -----------------------------------------------------------------------
+// s1 = sum dyp*gamma, s2 = sum dyp*gamma*xhat over each (sample, group); dyp = dy * [a*x+b > 0]
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                    const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta,
+                                                                    const float* __restrict__ stats,
+                                                                    float* __restrict__ partial, int P, int C,
+                                                                    int splits) {
+  constexpr int V = Vec<T>::N;
+  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+  const int n = blockIdx.y, split = blockIdx.x;
+  if (threadIdx.x < GN_GROUPS) {
+    s_mean[threadIdx.x] = stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 0];
+    s_rstd[threadIdx.x] = stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 1];
+  }
+  __syncthreads();
+  const int cpg = C / GN_GROUPS;
+  const T* xn = x + (size_t)n * P * C;
+  const T* dyn = dy + (size_t)n * P * C;
+  gn_reduce_slab<T>(P, C, split, splits, partial + (size_t)n * splits * GN_GROUPS * 2,
+                    [&](int p, int c0, float* a, float* b) {
+                      Vec<T> vx, vd; vx.load(xn + (size_t)p * C + c0); vd.load(dyn + (size_t)p * C + c0);
+                      float fx[V], fd[V]; vx.unpack(fx); vd.unpack(fd);
+#pragma unroll
+                      for (int i = 0; i < V; ++i) {
+                        const int c = c0 + i, g = c / cpg;
+                        const float ga = gamma[c], sa = s_rstd[g] * ga, sb = beta[c] - s_mean[g] * sa;
+                        const float pre = fmaf(sa, fx[i], sb);
+                        const float dg = pre > 0.f ? fd[i] * ga : 0.f;
+                        const float xh = (fx[i] - s_mean[g]) * s_rstd[g];
+                        a[i] += dg; b[i] += dg * xh;
+                      }
+                    });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                   const T* __restrict__ addend, T* __restrict__ dx,
+                                                                   const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta,
+                                                                   const float* __restrict__ stats,
+                                                                   const float* __restrict__ partial, int P, int C,
+                                                                   int splits) {
+  constexpr int V = Vec<T>::N;
+  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS], s_1[GN_GROUPS], s_2[GN_GROUPS];
+  const int n = blockIdx.y;
+  if (threadIdx.x < GN_GROUPS) {
+    s_mean[threadIdx.x] = stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 0];
+    s_rstd[threadIdx.x] = stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 1];
+    const float* pn = partial + (size_t)n * splits * GN_GROUPS * 2;
+    float a = 0.f, b = 0.f;
+    for (int k = 0; k < splits; ++k) { a += pn[(k * GN_GROUPS + threadIdx.x) * 2]; b += pn[(k * GN_GROUPS + threadIdx.x) * 2 + 1]; }
+    const float inv_m = 1.0f / ((float)P * (C / GN_GROUPS));
+    s_1[threadIdx.x] = a * inv_m;
+    s_2[threadIdx.x] = b * inv_m;
+  }
+  __syncthreads();
+  const int cols = C / V, cpg = C / GN_GROUPS;
+  const int p0 = (int)(((long long)P * blockIdx.x) / gridDim.x), p1 = (int)(((long long)P * (blockIdx.x + 1)) / gridDim.x);
+  const int cpt = cols < GN_THREADS ? cols : GN_THREADS, rpi = GN_THREADS / cpt;
+  const int tcol = threadIdx.x % cpt, trow = threadIdx.x / cpt;
+  const size_t base = (size_t)n * P * C;
+  for (int col = tcol; col < cols; col += cpt) {
+    float ga[V], sa[V], sb[V], mu[V], rs[V], m1[V], m2[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = col * V + i, g = c / cpg;
+      ga[i] = gamma[c]; mu[i] = s_mean[g]; rs[i] = s_rstd[g];
+      sa[i] = rs[i] * ga[i]; sb[i] = beta[c] - mu[i] * sa[i];
+      m1[i] = s_1[g]; m2[i] = s_2[g];
+    }
+    for (int p = p0 + trow; p < p1; p += rpi) {
+      const size_t off = base + (size_t)p * C + col * V;
+      Vec<T> vx, vd; vx.load(x + off); vd.load(dy + off);
+      float fx[V], fd[V], fo[V]; vx.unpack(fx); vd.unpack(fd);
+      if (addend != nullptr) { Vec<T> va; va.load(addend + off); va.unpack(fo); }
+      else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) fo[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float pre = fmaf(sa[i], fx[i], sb[i]);
+        const float dg = pre > 0.f ? fd[i] * ga[i] : 0.f;
+        const float xh = (fx[i] - mu[i]) * rs[i];
+        fo[i] += rs[i] * (dg - m1[i] - xh * m2[i]);
+      }
+      Vec<T> vo; vo.pack(fo); vo.store(dx + off);
+    }
+  }
+}
+
+void launch_gn_relu_backward(const void* dy, const void* x, const void* addend, void* dx, const float* gamma,
+                             const float* beta, const float* stats, float* partial, int N, int P, int C, bool bf16,
+                             cudaStream_t st) {
+  const int splits = gn_splits(P, C, bf16);
+  DISPATCH_T(bf16, (gn_bwd_reduce_kernel<T><<<dim3(splits, N), GN_THREADS, 0, st>>>(
+                       (const T*)dy, (const T*)x, gamma, beta, stats, partial, P, C, splits)));
+  DISPATCH_T(bf16, (gn_bwd_apply_kernel<T><<<dim3(apply_slabs(P, C, Vec<T>::N), N), GN_THREADS, 0, st>>>(
+                       (const T*)dy, (const T*)x, (const T*)addend, (T*)dx, gamma, beta, stats, partial, P, C, splits)));
+}
+
+// ------------------------------------------------------------------------------------
+// ConstantPad2d(1, 0) + MaxPool2d(3, stride 2): first max in row-major window order wins
+// (ATen: `val > maxval`), the zero padding is a real candidate.
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int8_t* __restrict__ amax, int Hs,
+                                   int Ws, int C, size_t total_vec) {
+  constexpr int V = Vec<T>::N;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int cols = C / V, Ho = Hs / 2, Wo = Ws / 2;
+  const int col = (int)(i % cols);
+  size_t r = i / cols;
+  const int ox = (int)(r % Wo); r /= Wo;
+  const int oy = (int)(r % Ho);
+  const size_t n = r / Ho;
+  float best[V]; int bi[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { best[k] = -INFINITY; bi[k] = 0; }
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = 2 * oy + ky - 1, xx = 2 * ox + kx - 1;   // unpadded coords
+      float f[V];
+      if (yy >= 0 && yy < Hs && xx >= 0 && xx < Ws) {
+        Vec<T> v; v.load(x + ((n * Hs + yy) * Ws + xx) * (size_t)C + col * V); v.unpack(f);
+      } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) f[k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k)
+        if (f[k] > best[k]) { best[k] = f[k]; bi[k] = ky * 3 + kx; }
+    }
+  Vec<T> o; o.pack(best); o.store(y + i * V);
+  if (amax != nullptr) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) amax[i * V + k] = (int8_t)bi[k];
+  }
+}
+
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const int8_t* __restrict__ amax, T* __restrict__ dx,
+                                   int Hs, int Ws, int C, size_t total_vec) {
+  constexpr int V = Vec<T>::N;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int cols = C / V, Ho = Hs / 2, Wo = Ws / 2;
+  const int col = (int)(i % cols);
+  size_t r = i / cols;
+  const int xx = (int)(r % Ws); r /= Ws;
+  const int yy = (int)(r % Hs);
+  const size_t n = r / Hs;
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  // windows (oy, ox) with 2*oy - 1 <= yy <= 2*oy + 1
+  for (int oy = (yy) / 2; oy <= (yy + 1) / 2; ++oy) {
+    if (oy < 0 || oy >= Ho) continue;
+    const int ky = yy - 2 * oy + 1;
+    if (ky < 0 || ky > 2) continue;
+    for (int ox = (xx) / 2; ox <= (xx + 1) / 2; ++ox) {
+      if (ox < 0 || ox >= Wo) continue;
+      const int kx = xx - 2 * ox + 1;
+      if (kx < 0 || kx > 2) continue;
+      const size_t o = (((n * Ho + oy) * Wo + ox) * (size_t)cols + col) * V;
+      Vec<T> v; v.load(dy + o);
+      float f[V]; v.unpack(f);
+      const int want = ky * 3 + kx;
+#pragma unroll
+      for (int k = 0; k < V; ++k)
+        if (amax[o + k] == want) acc[k] += f[k];
+    }
+  }
+  Vec<T> out; out.pack(acc); out.store(dx + i * V);
+}
+
+void launch_maxpool_forward(const void* x, void* y, int8_t* amax, int N, int Hs, int Ws, int C, bool bf16,
+                            cudaStream_t st) {
+  DISPATCH_T(bf16, {
+    size_t total = (size_t)N * (Hs / 2) * (Ws / 2) * (C / Vec<T>::N);
+    maxpool_fwd_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const T*)x, (T*)y, amax, Hs, Ws, C, total);
+  });
+}
+void launch_maxpool_backward(const void* dy, const int8_t* amax, void* dx, int N, int Hs, int Ws, int C, bool bf16,
+                             cudaStream_t st) {
+  DISPATCH_T(bf16, {
+    size_t total = (size_t)N * Hs * Ws * (C / Vec<T>::N);
+    maxpool_bwd_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const T*)dy, amax, (T*)dx, Hs, Ws, C, total);
+  });
+}
+
+// ------------------------------------------------------------------------------------
+// head
+// ------------------------------------------------------------------------------------
+// pooled[n][c] = (1/P) sum_p relu(a*x+b).  grid (C/(V*32), N), 32 column-threads x 8 row-threads
+template <typename T>
+__global__ void head_pool_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, const float* __restrict__ stats,
+                                 float* __restrict__ pooled, int P, int C) {
+  constexpr int V = Vec<T>::N;
+  __shared__ float sm[8][32][V];
+  const int n = blockIdx.y, col = blockIdx.x * 32 + threadIdx.x, cpg = C / GN_GROUPS;
+  float a[V], b[V], acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = col * V + i, g = c / cpg;
+    const float mean = stats[((size_t)n * GN_GROUPS + g) * 2], rstd = stats[((size_t)n * GN_GROUPS + g) * 2 + 1];
+    a[i] = rstd * gamma[c]; b[i] = beta[c] - mean * a[i]; acc[i] = 0.f;
+  }
+  for (int p = threadIdx.y; p < P; p += 8) {
+    Vec<T> v; v.load(x + ((size_t)n * P + p) * C + col * V);
+    float f[V]; v.unpack(f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] += fmaxf(fmaf(a[i], f[i], b[i]), 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) sm[threadIdx.y][threadIdx.x][i] = acc[i];
+  __syncthreads();
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float t = 0.f;
+      for (int r = 0; r < 8; ++r) t += sm[r][threadIdx.x][i];
+      pooled[(size_t)n * C + col * V + i] = t / P;
+    }
+  }
+}
+void launch_head_pool(const void* x, const float* gamma, const float* beta, const float* stats, float* pooled,
+                      int N, int P, int C, bool bf16, cudaStream_t st) {
+  DISPATCH_T(bf16, (head_pool_kernel<T><<<dim3(C / (Vec<T>::N * 32), N), dim3(32, 8), 0, st>>>(
+                       (const T*)x, gamma, beta, stats, pooled, P, C)));
+}
+
+// logits[n][k] = b[k] + sum_c pooled[n][c] * w[k][c]; one warp per (n,k)
+__global__ void fc_fwd_kernel(const float* __restrict__ pooled, const float* __restrict__ w,
+                              const float* __restrict__ b, float* __restrict__ logits, int N, int C, int K) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N * K) return;
+  const int n = warp / K, k = warp % K;
+  const float* pn = pooled + (size_t)n * C;
+  const float* wk = w + (size_t)k * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s = fmaf(pn[c], wk[c], s);
+  s = warp_sum(s);
+  if (lane == 0) logits[(size_t)n * K + k] = s + b[k];
+}
+void launch_fc_forward(const float* pooled, const float* w, const float* b, float* logits, int N, int C, int K,
+                       cudaStream_t st) {
+  const size_t threads = (size_t)N * K * 32;
+  fc_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(pooled, w, b, logits, N, C, K);
+}
+// dpooled[n][c] = sum_k dlogits[n][k] * w[k][c]   (dlogits is almost all zeros: skip them)
+__global__ void fc_bwd_kernel(const float* __restrict__ dl, const float* __restrict__ w, float* __restrict__ dp,
+                              int N, int C, int K) {
+  const int n = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float d = dl[(size_t)n * K + k];   // uniform across the CTA
+    if (d != 0.f) s = fmaf(d, w[(size_t)k * C + c], s);
+  }
+  dp[(size_t)n * C + c] = s;
+}
+void launch_fc_backward(const float* dlogits, const float* w, float* dpooled, int N, int C, int K, cudaStream_t st) {
+  fc_bwd_kernel<<<dim3((C + 255) / 256, N), 256, 0, st>>>(dlogits, w, dpooled, N, C, K);
+}
+template <typename T>
+__global__ void pool_grad_bcast_kernel(const float* __restrict__ dp, T* __restrict__ dy, int P, int C, size_t total_vec) {
+  constexpr int V = Vec<T>::N;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int cols = C / V, col = (int)(i % cols);
+  const size_t n = i / cols / P;
+  float f[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) f[k] = dp[n * C + col * V + k] / P;
+  Vec<T> v; v.pack(f); v.store(dy + i * V);
+}
+void launch_pool_grad_bcast(const float* dpooled, void* dy, int N, int P, int C, bool bf16, cudaStream_t st) {
+  DISPATCH_T(bf16, {
+    size_t total = (size_t)N * P * (C / Vec<T>::N);
+    pool_grad_bcast_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dpooled, (T*)dy, P, C, total);
+  });
+}
+
+// ------------------------------------------------------------------------------------
+// stride-2 spatial subsample (1x1 stride-2 shortcut conv = subsample + GEMM) and adjoint
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void subsample2_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, size_t total_vec) {
+  constexpr int V = Vec<T>::N;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int cols = C / V, Ho = (H + 1) / 2, Wo = (W + 1) / 2, col = (int)(i % cols);
+  size_t r = i / cols;
+  const int ox = (int)(r % Wo); r /= Wo;
+  const int oy = (int)(r % Ho);
+  const size_t n = r / Ho;
+  Vec<T> v; v.load(x + ((n * H + 2 * oy) * W + 2 * ox) * (size_t)C + col * V);
+  v.store(y + i * V);
+}
+template <typename T>
+__global__ void subsample2_adj_kernel(const T* __restrict__ dy, T* __restrict__ dx, int H, int W, int C, size_t total_vec) {
+  constexpr int V = Vec<T>::N;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int cols = C / V, Ho = (H + 1) / 2, Wo = (W + 1) / 2, col = (int)(i % cols);
+  size_t r = i / cols;
+  const int ox = (int)(r % Wo); r /= Wo;
+  const int oy = (int)(r % Ho);
+  const size_t n = r / Ho;
+  T* dst = dx + ((n * H + 2 * oy) * W + 2 * ox) * (size_t)C + col * V;
+  Vec<T> a, b; a.load(dy + i * V); b.load(dst);
+  float fa[V], fb[V]; a.unpack(fa); b.unpack(fb);
+#pragma unroll
+  for (int k = 0; k < V; ++k) fb[k] += fa[k];
+  b.pack(fb); b.store(dst);
+}
+void launch_subsample2(const void* x, void* y, int N, int H, int W, int C, bool bf16, cudaStream_t st) {
+  DISPATCH_T(bf16, {
+    size_t total = (size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / Vec<T>::N);
+    subsample2_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const T*)x, (T*)y, H, W, C, total);
+  });
+}
+void launch_subsample2_adjoint_add(const void* dy, void* dx, int N, int H, int W, int C, bool bf16, cudaStream_t st) {
+  DISPATCH_T(bf16, {
+    size_t total = (size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / Vec<T>::N);
+    subsample2_adj_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const T*)dy, (T*)dx, H, W, C, total);
+  });
+}
+
+}  // namespace dp
