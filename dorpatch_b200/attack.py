@@ -1,0 +1,389 @@
+"""DorPatch patch generation on the native B200 engine -- host control flow.
+
+Drop-in for /root/reference/attack.py: ``DorPatch().generate(...)`` keeps the reference's
+signature (attack.py:51-53), side effects (prints, stage-0 artefacts in the parent directory,
+RNG consumption) and return value.  Everything numeric in the hot loop (attack.py:184-247,
+332-342) runs in libdorpatch.so through ``dorpatch_b200.engine.Engine``; what stays here is
+the scalar state machine of attack.py:249-330 (failed-mask set, best snapshot, patience / lr
+decay, coefficient adaptation) and the numpy sampling of attack.py:193-204, both of which
+depend on the legacy global numpy RNG and Python-float arithmetic and are O(S) per step.
+
+Semantics beyond the reference:
+  * B > 1 runs B independent single-image problems side by side (the reference is
+    batch-size-1 only); all scalar state is per image.  B == 1 reproduces the reference's
+    control flow and RNG stream exactly.
+  * the two ``set_target(preds_adv)`` call sites with a missing argument (attack.py:155,359,
+    a TypeError in the reference) pass the label.
+  * EOT sharding: with torch.distributed initialised, each rank evaluates S/world samples and
+    the ranks all-reduce the patch gradient once per step.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import masks as _masks
+from .utils import unwrap_native
+
+PATIENCE = 200
+SCALE_UP = 1.2
+SCALE_DOWN = np.sqrt(SCALE_UP ** 3)
+
+
+# ----------------------------------------------------------------------------------------
+# public helpers kept for API compatibility with the reference module
+# ----------------------------------------------------------------------------------------
+class CW_loss():
+    """attack.py:10-23 (torch ops; the hot loop uses the fused native K4 kernel instead)."""
+
+    def __init__(self, num_classes, targeted=False, confidence=0):
+        self.num_classes, self.targeted, self.confidence = num_classes, targeted, confidence
+
+    def __call__(self, logits, y):
+        idx = torch.arange(logits.shape[0], device=logits.device)
+        real = logits[idx, y]
+        masked = logits.clone()
+        masked[idx, y] = -1e4
+        other = masked.max(1)[0]
+        margin = (other - real) if self.targeted else (real - other)
+        return torch.clamp(self.confidence + margin, min=0.)
+
+
+def get_mask_set(img_size, dropout_size, dropout):
+    """attack.py:25-31; returns the bool mask tensor like the reference (API compatibility)."""
+    from .defenses.PatchCleanser import MaskWindow
+    mw = MaskWindow(img_size, dropout_size)
+    return mw.mask_set if dropout == 1 else (mw.double_mask_set if dropout == 2 else None)
+
+
+def local_variance(x):
+    """attack.py:33-39 incl. its raw last row / column (values only)."""
+    lr = torch.cat([(x[..., :, :-1] - x[..., :, 1:]).abs(), x[..., :, -1:]], dim=-1)
+    ud = torch.cat([(x[..., :-1, :] - x[..., 1:, :]).abs(), x[..., -1:, :]], dim=-2)
+    return lr + ud, lr, ud
+
+
+def min_var_weighted_variance(x):
+    """attack.py:41-45 (values only)."""
+    lv, lr, ud = local_variance(x)
+    return lv * torch.minimum(lr, ud)
+
+
+# ----------------------------------------------------------------------------------------
+class _ImageState(object):
+    """The scalars the reference keeps in local variables, for one image."""
+
+    def __init__(self, lr, structured, y, targeted, rng):
+        self.lr0 = np.float32(lr)
+        self.coeff_group_lasso = 1e-5            # attack.py:87
+        self.structured = structured
+        self.y = int(y)
+        self.targeted = bool(targeted)           # the `targeted` variable (scan semantics)
+        self.crit_targeted = bool(targeted)      # self.criterion.targeted
+        self.failed = []
+        self.certifiable = False
+        self.rng = rng
+        self.reset()
+
+    def reset(self):                             # attack.py:129-132
+        self.lr = np.float32(self.lr0)
+        self.loss_best = np.float32(np.inf)
+        self.not_decay = 0
+        self.num_failure = np.inf
+        self.active = True
+
+    def sample(self, i, n_mask, S):              # attack.py:193-204
+        n_ff = 0 if i < 1000 else min(len(self.failed), S // 2)
+        parts = []
+        if n_ff > 0:
+            parts.append(self.rng.choice(self.failed, n_ff, replace=False))
+        if S - n_ff > 0:
+            parts.append(self.rng.choice(np.arange(n_mask), S - n_ff, replace=False))
+        return np.concatenate(parts), n_ff
+
+    def bookkeeping(self, stage, i, loss_adv, idx, n_ff, loss_target):   # attack.py:249-308
+        ok = loss_adv < np.float32(1e-1)
+        gone = idx[:n_ff][ok[:n_ff]]
+        if len(gone) > 0:
+            self.failed = np.setdiff1d(self.failed, gone).tolist()
+        new = idx[n_ff:][~ok[n_ff:]]
+        if len(new) > 0:
+            self.failed = np.unique(list(self.failed) + list(new)).tolist()
+        n_failed = len(self.failed)
+        self.certifiable = n_failed == 0
+        if n_failed < self.num_failure:
+            self.loss_best = np.float32(np.inf)
+        loss_target = np.float32(loss_target)
+        with np.errstate(invalid="ignore"):
+            improved = bool(n_failed <= self.num_failure and
+                            np.float32(loss_target - self.loss_best) < np.float32(-1e-3))
+        if improved:
+            self.num_failure, self.loss_best, self.not_decay = n_failed, loss_target, 0
+        else:
+            self.not_decay += 1
+        plateau = self.not_decay > PATIENCE
+        good = bool(ok.all()) and self.certifiable
+        if stage == 0 and i > 200:
+            self.coeff_group_lasso = self.coeff_group_lasso * SCALE_UP if good else self.coeff_group_lasso / SCALE_DOWN
+        else:
+            self.structured = self.structured * SCALE_UP if good else self.structured / SCALE_DOWN
+        if plateau:
+            self.lr = max(np.float32(self.lr * np.float32(0.1)), np.float32(.1 / 256.))
+            self.not_decay = 0
+        return improved, bool(self.lr < np.float32(1e-3))
+
+
+def _pick_target(preds, label):
+    """attack.py:106-122 for one image; returns (label, switched)."""
+    preds = np.asarray(preds).reshape(-1)
+    wrong = preds[preds != label]
+    if wrong.size == 0:
+        return label, False
+    if wrong.size > 1:
+        vals, counts = np.unique(wrong, return_counts=True)     # torch.mode: smallest of the most frequent
+        return int(vals[np.argmax(counts)]), True
+    return int(wrong[0]), True
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 \
+            and os.environ.get("DORPATCH_SHARD", "eot") == "eot":
+        return dist
+    return None
+
+
+class DorPatch(object):
+    def __init__(self):
+        self.last_stats = {}
+
+    # ------------------------------------------------------------------------------------
+    def generate(self, model, x, patch_budget, n_classes, save_dir, batch_id, y=None, targeted=False,
+                 lr=1e-2, confidence=1e-1, clip_min=0, clip_max=1, max_iterations=5000, basic_unit=7,
+                 selection='topk', dropout=2, sampling_size=128, density=1e-3, structured=1e-3, eps=4., dual=False,
+                 **kwargs):
+        if basic_unit != 7:
+            raise NotImplementedError("the native kernels are built for basic_unit=7")
+        if selection != 'topk':
+            raise NotImplementedError("selection=%r" % (selection,))
+        if dropout not in (1, 2):
+            raise NotImplementedError("dropout=%r (the reference's dropout=0 path is degenerate)" % (dropout,))
+        net = unwrap_native(model)
+        if not x.is_cuda:
+            raise RuntimeError("DorPatch.generate needs CUDA tensors: the hot loop exists only as native sm_100a kernels")
+        x = x.contiguous().float()
+        B, _, H, W = x.shape
+        eng = net.engine(W, max_images=B)
+        dev = x.device
+        dist = _dist()
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+
+        adv_mask = torch.rand([B, 1, H, W]).to(dev)              # attack.py:59 (CPU generator)
+        adv_pattern = torch.rand(x.shape).to(dev)                # attack.py:60
+        mask_best = torch.zeros_like(adv_mask)
+        pattern_best = torch.zeros_like(adv_pattern)
+        if y is None:                                            # attack.py:67-69
+            y = torch.from_numpy(eng.predict(x).astype(np.int64))
+        y = [int(v) for v in (y.tolist() if torch.is_tensor(y) else y)]
+        # the reference constructs two throw-away Conv2d modules whose kaiming init draws
+        # 49 + (W/8)^2 values from the CPU generator (attack.py:72-80)
+        torch.nn.Conv2d(1, 1, basic_unit, stride=basic_unit, bias=False)
+        torch.nn.Conv2d(1, 1, W // 8, stride=W // 8, bias=False)
+
+        table = _masks.universe(W, dropout)                      # attack.py:83-85 as rectangles
+        n_mask = table.shape[0]
+        S = min(sampling_size, n_mask)
+        if S % world != 0:
+            raise ValueError("sampling_size=%d must be divisible by the world size %d" % (S, world))
+        S_loc = S // world
+        all_rects = _masks.gather(table, np.arange(n_mask))      # [n_mask,4,4] for the scans
+
+        if B == 1:
+            rngs = [np.random]                                   # the global legacy stream, as the reference
+        else:
+            rngs = [np.random.RandomState(int(np.random.randint(0, 2 ** 31 - 1))) for _ in range(B)]
+        st = [_ImageState(lr, structured, y[b], targeted, rngs[b]) for b in range(B)]
+        dir_0 = os.path.dirname(save_dir.rstrip('/')) if save_dir else None
+        G = torch.zeros_like(x)
+        last_preds = None
+        steps = 0
+
+        def scan(b, adv_x):                                      # collect_failure, attack.py:384-406
+            preds = eng.predict(adv_x[b:b + 1], n_mask, all_rects)
+            f = preds == st[b].y
+            if st[b].targeted:
+                f = ~f
+            failed = np.nonzero(f)[0].tolist()
+            print(">> %d failures collected!" % len(failed))
+            return failed
+
+        for stage in range(2):
+            print('============= Stage %d =============' % stage)
+            for s in st:
+                s.reset()
+            if stage == 0 and dir_0 and os.path.exists(os.path.join(dir_0, "adv_mask_%d.pt" % batch_id)):
+                mask_best = torch.load(os.path.join(dir_0, "adv_mask_%d.pt" % batch_id)).to(dev)
+                pattern_best = torch.load(os.path.join(dir_0, "adv_pattern_%d.pt" % batch_id)).to(dev)
+                continue
+            if stage == 1:                                       # attack.py:143-165
+                adv_x, _, _ = eng.paste(x, mask_best, pattern_best, eps)
+                if any(not s.targeted for s in st):
+                    p1 = eng.predict(adv_x)
+                    for b, s in enumerate(st):
+                        if not s.targeted:
+                            s.targeted = True
+                            s.y, sw = _pick_target(p1[b:b + 1], s.y)
+                            s.crit_targeted = s.crit_targeted or sw
+                pattern_best = adv_x.clone()
+                torch.nn.Conv2d(1, 1, basic_unit, stride=basic_unit, bias=False)   # attack.py:365 RNG draw
+                adv_mask = self.patch_selection(mask_best, patch_budget, basic_unit, selection)
+                mask_best = adv_mask.clone()
+                adv_pattern = pattern_best.clone()
+            adv_x = adv_x_prev = None
+            for i in range(max_iterations):
+                if stage == 0 and i == 500:                      # attack.py:169-182
+                    for b, s in enumerate(st):
+                        if s.targeted or not s.active:
+                            continue
+                        s.targeted = True
+                        y_new, sw = _pick_target(last_preds[b], s.y)
+                        if y_new != s.y:
+                            s.y = y_new
+                            print(">> switch to targeted attack to category {:3d} at iteration: {:4d}".format(s.y, i))
+                        s.crit_targeted = s.crit_targeted or sw
+                        s.reset()
+                        s.failed = scan(b, adv_x_prev)
+                if stage == 0 and i == 499 and any(s.active and not s.targeted for s in st):
+                    adv_x_prev, _, _ = eng.paste(x, adv_mask, adv_pattern, eps)   # the `adv_x` step 500 scans
+                if i % 100 == 0:                                 # attack.py:187-190
+                    adv_x, _, _ = eng.paste(x, adv_mask, adv_pattern, eps)
+                    for b, s in enumerate(st):
+                        if s.active:
+                            s.failed = scan(b, adv_x)
+                idx = np.zeros((B, S), np.int64)
+                idx2 = np.zeros((B, S), np.int64) if dual else None
+                nff = [0] * B
+                for b, s in enumerate(st):
+                    if s.active:
+                        idx[b], nff[b] = s.sample(i, n_mask, S)
+                        if dual:
+                            idx2[b], _ = s.sample(i, n_mask, S)
+                sl = slice(rank * S_loc, (rank + 1) * S_loc)
+                rects = _masks.gather(table, idx[:, sl], idx2[:, sl] if dual else None)
+                structured_used = [s.structured for s in st]
+                coeff_used = [s.coeff_group_lasso for s in st]
+                r = eng.attack_grad(x, adv_mask, adv_pattern, rects, [s.y for s in st],
+                                    [s.crit_targeted for s in st], confidence, eps, stage, G, S_total=S)
+                loss_adv, preds = r["loss_adv"], r["preds"]
+                if dist:                                         # one all-reduce of the patch gradient per step
+                    dist.all_reduce(G)
+                    pack = torch.from_numpy(np.concatenate([loss_adv, preds.astype(np.float32)], 1)).to(dev)
+                    outs = [torch.empty_like(pack) for _ in range(world)]
+                    dist.all_gather(outs, pack)
+                    loss_adv = np.concatenate([o[:, :S_loc].cpu().numpy() for o in outs], 1)
+                    preds = np.concatenate([o[:, S_loc:].cpu().numpy() for o in outs], 1).astype(np.int32)
+                last_preds = preds
+                loss_target = r["group_lasso"] if stage == 0 else r["loss_struc"]
+                lr_used = np.zeros(B, np.float32)
+                for b, s in enumerate(st):
+                    if not s.active:
+                        continue
+                    improved, stop = s.bookkeeping(stage, i, loss_adv[b], idx[b], nff[b], loss_target[b])
+                    if improved:                                 # best snapshot stays on the device
+                        if stage == 0:
+                            mask_best[b].copy_(adv_mask[b])
+                        pattern_best[b].copy_(adv_pattern[b])
+                    if stop:
+                        print("early stop at iteration: {:4d}".format(i))
+                        if np.isinf(s.loss_best):
+                            mask_best[b].copy_(adv_mask[b])
+                            pattern_best[b].copy_(adv_pattern[b])
+                        s.active = False
+                    else:
+                        lr_used[b] = s.lr
+                steps += 1
+                if not any(s.active for s in st):
+                    break
+                if i % 20 == 0:                                  # attack.py:317-330
+                    ys = np.asarray([s.y for s in st])[:, None]
+                    acc = float((preds == ys).sum()) / (B * S) * 100
+                    coef_st = np.asarray(structured_used, np.float32)
+                    total = loss_adv.mean(1) + np.where(coef_st != 0, coef_st * r["loss_struc"], 0)
+                    if stage == 0:
+                        total = total + np.float32(density) * r["loss_density"] + \
+                            np.asarray(coeff_used, np.float32) * r["group_lasso"]
+                    msg = "iteration: {:4d}, accuracy: {:.2f}, loss: {:.2f}, adv: {:.2f}, l2 norm: {:.2f}, structural: {:.2f}".format(
+                        i, acc, float(total.mean()), float(loss_adv.mean()),
+                        float(np.minimum(r["l2"], eps).mean()), float(r["loss_struc"].mean()))
+                    if stage == 0:
+                        msg += ", group lasso: {:.2f}, density: {:.2f}".format(
+                            float(r["group_lasso"].mean()), float(r["loss_density"].mean()))
+                    print(msg)
+                eng.attack_update(x, adv_mask, adv_pattern, G, lr_used, structured_used, coeff_used, density, stage,
+                                  clip_min, clip_max)            # attack.py:332-342
+            for b, s in enumerate(st):                           # attack.py:344-346
+                if s.active and np.isinf(s.loss_best):
+                    mask_best[b].copy_(adv_mask[b])
+                    pattern_best[b].copy_(adv_pattern[b])
+            if stage == 0:                                       # attack.py:348-359
+                if dir_0 and rank == 0:
+                    os.makedirs(dir_0, exist_ok=True)
+                    torch.save(mask_best, os.path.join(dir_0, "adv_mask_%d.pt" % batch_id))
+                    torch.save(pattern_best, os.path.join(dir_0, "adv_pattern_%d.pt" % batch_id))
+                for b, s in enumerate(st):
+                    if not s.targeted and last_preds is not None:
+                        s.y, sw = _pick_target(last_preds[b], s.y)
+                        s.crit_targeted = s.crit_targeted or sw
+        self.last_stats = dict(steps=steps, samples_per_step=B * S, final_labels=[s.y for s in st])
+        return mask_best, pattern_best
+
+    # ------------------------------------------------------------------------------------
+    def patch_selection(self, mask, patch_budget, basic_unit=7, selection='topk'):
+        """attack.py:363-382: top-k 7x7 groups with positive importance -> binary mask.
+        Window sums on the device (native kernel); the k-of-1024 selection on the host."""
+        if selection != 'topk':
+            raise NotImplementedError("selection=%r" % (selection,))
+        from .runtime import shared_engine
+        B, _, H, W = mask.shape
+        eng = shared_engine(W, B)
+        imp = eng.window_sum(mask.contiguous().float(), basic_unit)                   # [B, (H/7)*(W/7)]
+        num_group = int(np.floor((H * W * patch_budget) / (basic_unit ** 2)))
+        sel = np.zeros_like(imp)
+        for b in range(B):
+            order = np.argsort(-imp[b], kind="stable")[:num_group]
+            sel[b, order[imp[b, order] > 0]] = 1
+        sel = torch.from_numpy(sel.reshape(B, 1, H // basic_unit, W // basic_unit)).to(mask.device)
+        return sel.repeat_interleave(basic_unit, dim=2).repeat_interleave(basic_unit, dim=3)
+
+    def collect_failure(self, adv_x, y, mask_set_universe, targeted, model, batch_size=128, transforms=None):
+        """attack.py:384-406 with the reference's signature: `mask_set_universe` may be the bool
+        tensor of the reference or an int16 rectangle table [n,2,4]."""
+        if isinstance(mask_set_universe, np.ndarray):
+            net = unwrap_native(model)
+            eng = net.engine(adv_x.shape[-1], max_images=adv_x.shape[0])
+            n = mask_set_universe.shape[0]
+            rects = _masks.gather(mask_set_universe, np.arange(n))
+            B = adv_x.shape[0]
+            preds = eng.predict(adv_x.contiguous().float(), n, np.broadcast_to(rects, (B,) + rects.shape))
+            yv = np.asarray(y.tolist() if torch.is_tensor(y) else y).reshape(B, -1)[:, :1]
+            f = preds.reshape(B, n) == yv
+            if targeted:
+                f = ~f
+            failed = np.nonzero(f.any(0))[0].tolist()
+        else:
+            n = mask_set_universe.size(0)
+            failed = []
+            with torch.no_grad():
+                for j in range(int(np.ceil(n / batch_size))):
+                    ms = mask_set_universe[j * batch_size: min((j + 1) * batch_size, n)]
+                    xm = (adv_x[:, None] * ms + 0.5 * ~ms).view((-1,) + adv_x.shape[1:])
+                    if transforms is not None:
+                        xm = transforms(xm)
+                    preds = model(xm).argmax(-1)
+                    f = preds == y.view((adv_x.shape[0], batch_size))[:, :ms.size(0)].reshape(-1)
+                    if targeted:
+                        f = ~f
+                    failed.append((f.nonzero().view(-1) % ms.size(0) + j * batch_size).unique())
+                failed = torch.cat(failed, 0).cpu().numpy().tolist()
+        print(">> %d failures collected!" % len(failed))
+        return failed

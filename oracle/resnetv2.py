@@ -73,9 +73,13 @@ def random_init(seed=0, num_classes=1000, affine_jitter=0.0):
         elif name == "head.fc.bias":
             params[name] = torch.zeros(shp)
         elif name.endswith("weight"):  # GroupNorm gamma
-            params[name] = torch.ones(shp) + affine_jitter * torch.randn(shp, generator=g)
+            params[name] = torch.ones(shp)
+            if affine_jitter:
+                params[name] += affine_jitter * torch.randn(shp, generator=g)
         else:  # GroupNorm beta
-            params[name] = torch.zeros(shp) + affine_jitter * torch.randn(shp, generator=g)
+            params[name] = torch.zeros(shp)
+            if affine_jitter:
+                params[name] += affine_jitter * torch.randn(shp, generator=g)
     return params
 
 

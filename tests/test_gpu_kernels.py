@@ -1,0 +1,204 @@
+"""GPU parity tests: every native kernel / engine entry point (called through the C ABI)
+against the CPU oracle on the same seeded inputs.  Tolerances are stated per test."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import attack as OA
+from oracle import masks as OM
+from oracle import resnetv2 as OR
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rand(shape, seed):
+    return torch.rand(shape, generator=torch.Generator().manual_seed(seed))
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def _rects_for(H, idx, dropout=2, idx2=None):
+    table = OM.rects_to_array(OM.universe_rects(H, dropout))
+    out = np.zeros(np.asarray(idx).shape + (4, 4), np.int16)
+    out[..., 0:2, :] = table[np.asarray(idx)]
+    if idx2 is not None:
+        out[..., 2:4, :] = table[np.asarray(idx2)]
+    return out
+
+
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H", [56, 224])
+def test_paste_matches_clip(engine_factory, H):
+    """utils.clip + add.  fp32; tolerance 2e-6 abs (the L2 norm reduction order differs)."""
+    e = engine_factory(img=H, precision="fp32", chunk=4, max_images=4)
+    B = 3
+    x, m, p = _rand((B, 3, H, H), 1), _rand((B, 1, H, H), 2), _rand((B, 3, H, H), 3)
+    m[1] *= 0.01          # image 1: ||delta|| < eps -> scale exactly 1
+    m[2] *= 0.0           # image 2: zero delta -> eps/0 = inf -> clipped to 1
+    adv, l2, sc = e.paste(x.to(DEV), m.to(DEV), p.to(DEV), 4.0)
+    torch.cuda.synchronize()
+    ref = x + OA.clip_paste(m, p, x, 4.0)
+    ref_l2 = torch.norm(m * (p - x), p=2, dim=(1, 2, 3))
+    assert np.allclose(l2, ref_l2.numpy(), rtol=1e-5)
+    assert sc[1] == 1.0 and sc[2] == 1.0 and sc[0] < 1.0
+    assert (adv.cpu() - ref).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("H,S", [(56, 5), (224, 7)])
+def test_expand_matches_occlude_normalise(engine_factory, precision, H, S):
+    """K1 (non-fused entry): (occlude(img) - 0.5)/0.5 in NHWC.  fp32: bit-exact;
+    bf16: equal to the bf16 rounding of the fp32 result."""
+    e = engine_factory(img=H, precision=precision, chunk=4, max_images=4)
+    B = 2
+    img = _rand((B, 3, H, H), 5)
+    rng = np.random.RandomState(0)
+    idx, idx2 = rng.randint(0, 2520, (B, S)), rng.randint(0, 2520, (B, S))
+    idx[0, 0] = 0
+    rects = _rects_for(H, idx, 2, idx2)
+    rects[1, 1] = 0                                        # one sample without any occluder
+    out = e.expand(img.to(DEV), S, rects)
+    torch.cuda.synchronize()
+    uni = torch.from_numpy(OM.rects_to_bool(OM.universe_rects(H, 2), H))
+    ref = OA.occlude(OA.occlude(img[:, None], uni[idx.reshape(-1)].reshape(B, S, 1, H, H)),
+                     uni[idx2.reshape(-1)].reshape(B, S, 1, H, H))
+    ref[1, 1] = img[1]
+    ref = ((ref - 0.5) / 0.5).reshape(B * S, 3, H, H).permute(0, 2, 3, 1)
+    got = out.float().cpu()
+    assert got.shape[-1] == e.c_pad
+    assert (got[..., 3:] == 0).all()
+    if precision == "fp32":
+        assert torch.equal(got[..., :3], ref)
+    else:
+        assert torch.equal(got[..., :3], ref.bfloat16().float())
+
+
+@pytest.mark.parametrize("precision,tol_logit,min_cos", [("fp32", 2e-3, 0.999), ("tf32", 3e-2, 0.99), ("bf16", 8e-2, 0.97)])
+def test_classifier_forward_backward(engine_factory, oracle_params, precision, tol_logit, min_cos):
+    """ResNetV2-50 logits and d/d(input) vs torch-CPU autograd on the oracle restatement.
+    fp32: |dlogit| <= 2e-3, grad cosine >= 0.999 (ReLU / max-pool ties flip on last-bit
+    differences, so gradients are compared by cosine, not element-wise)."""
+    H, N = 112, 3
+    e = engine_factory(img=H, precision=precision, chunk=8, max_images=4)
+    z = (_rand((N, 3, H, H), 11) - 0.5) * 2
+    dl = torch.zeros(N, 1000)
+    dl[torch.arange(N), torch.tensor([3, 500, 999])] = 1.0
+    dl[torch.arange(N), torch.tensor([7, 1, 0])] = -1.0
+    logits, dz = e.net_forward_backward(z.to(DEV), dl.to(DEV))
+    torch.cuda.synchronize()
+    zr = z.clone().requires_grad_(True)
+    ref = OR.forward_normalized(oracle_params, zr)
+    (ref * dl).sum().backward()
+    err = (logits.cpu() - ref.detach()).abs().max().item()
+    cos = _cos(dz.cpu(), zr.grad)
+    print("precision", precision, "logit err", err, "grad cos", cos, "rel", _rel(dz.cpu(), zr.grad))
+    assert err <= tol_logit, err
+    assert cos >= min_cos, cos
+
+
+def test_predict_matches_oracle(engine_factory, oracle_net):
+    """dp_predict (K1 + forward + argmax), fp32: logits within 2e-3 of the oracle and the
+    same argmax wherever the oracle's top-2 margin exceeds 1e-2."""
+    H, B, S = 112, 2, 5
+    e = engine_factory(img=H, precision="fp32", chunk=8, max_images=4)
+    img = _rand((B, 3, H, H), 21)
+    idx = np.random.RandomState(1).randint(0, 144, (B, S))
+    rects = _rects_for(H, idx, 1)
+    preds, logits = e.predict(img.to(DEV), S, rects, return_logits=True)
+    uni = torch.from_numpy(OM.rects_to_bool(OM.universe_rects(H, 1), H))
+    with torch.no_grad():
+        ref = oracle_net(OA.occlude(img[:, None], uni[idx.reshape(-1)].reshape(B, S, 1, H, H)).reshape(B * S, 3, H, H))
+    assert np.abs(logits - ref.numpy()).max() <= 2e-3
+    top2 = ref.topk(2, dim=1).values
+    sure = (top2[:, 0] - top2[:, 1]) > 1e-2
+    assert (torch.from_numpy(preds).long()[sure] == ref.argmax(1)[sure]).all()
+    # no-occlusion path (model(x))
+    p0 = e.predict(img.to(DEV))
+    with torch.no_grad():
+        r0 = oracle_net(img)
+    t2 = r0.topk(2, dim=1).values
+    s0 = (t2[:, 0] - t2[:, 1]) > 1e-2
+    assert (torch.from_numpy(p0).long()[s0] == r0.argmax(1)[s0]).all()
+
+
+@pytest.mark.parametrize("stage", [0, 1])
+def test_attack_step_matches_oracle(engine_factory, oracle_net, stage):
+    """One hot-loop iteration (attack.py:184-247 + :332-342), fp32 engine, B=2 x S=3, two
+    chunks.  loss_adv / regularisers: 2e-3 abs (rel 1e-4 for the lasso); gradients:
+    cosine >= 0.999 and sign agreement >= 99% where |g| is above 1e-3 of its max."""
+    H, B, S = 112, 2, 3
+    e = engine_factory(img=H, precision="fp32", chunk=4, max_images=4)
+    x, m, p = _rand((B, 3, H, H), 31), _rand((B, 1, H, H), 32), _rand((B, 3, H, H), 33)
+    if stage == 1:
+        m = (m > 0.8).float()
+    else:
+        m[0, 0, :7, :7] = 0.0                      # an all-zero 7x7 group -> NaN grad -> frozen (quirk Q5)
+    y = torch.tensor([17, 400])
+    targeted = [True, False]
+    idx = np.random.RandomState(3).randint(0, 2520, (B, S))
+    rects = _rects_for(H, idx, 2)
+    structured, coeff = [1e-3, 5e-4], [1e-5, 3e-5]
+    density = 1e-3
+    xd, md, pd = x.to(DEV), m.to(DEV).clone(), p.to(DEV).clone()
+    G = torch.zeros(B, 3, H, H, device=DEV)
+    r = e.attack_grad(xd, md, pd, rects, y.numpy(), targeted, 0.1, 4.0, stage, G)
+    gp, gm = torch.zeros_like(pd), torch.zeros_like(md)
+    lr = np.array([0.01, 0.02], np.float32)
+    e.attack_update(xd, md, pd, G, lr, structured, coeff, density, stage, grad_pattern_out=gp, grad_mask_out=gm)
+    torch.cuda.synchronize()
+
+    uni = torch.from_numpy(OM.rects_to_bool(OM.universe_rects(H, 2), H))
+    lvx = OA.local_variance(x)[0].mean(1)
+    o = OA.step_losses_and_grads(oracle_net, x, m, p, y, idx, uni, targeted, 1000, 0.1, structured, density,
+                                 coeff, stage, 4.0, lvx)
+    print("loss_adv", r["loss_adv"], o["loss_adv"].numpy())
+    assert np.abs(r["loss_adv"] - o["loss_adv"].numpy()).max() <= 2e-3
+    assert np.allclose(r["loss_struc"], o["loss_struc"].numpy(), rtol=1e-4, atol=1e-6)
+    top2 = o["logits"].topk(2, dim=1).values
+    sure = ((top2[:, 0] - top2[:, 1]) > 1e-2).numpy()
+    assert (r["preds"].reshape(-1)[sure] == o["logits"].argmax(1).numpy()[sure]).all()
+    if stage == 0:
+        assert np.allclose(r["loss_density"], o["loss_density"].numpy(), rtol=1e-4)
+        assert np.allclose(r["group_lasso"], o["group_lasso"].numpy(), rtol=1e-4)
+
+    def check_grad(name, got, ref):
+        ref = torch.nan_to_num(ref, nan=0.0)
+        got = torch.nan_to_num(got.cpu(), nan=0.0)
+        cos = _cos(got, ref)
+        big = ref.abs() > 1e-3 * ref.abs().max()
+        agree = (got.sign()[big] == ref.sign()[big]).float().mean().item()
+        print(name, "cos", cos, "sign agreement", agree)
+        assert cos >= 0.999, (name, cos)
+        assert agree >= 0.99, (name, agree)
+
+    check_grad("grad_pattern", gp, o["grad_pattern"])
+    # sign step
+    pref = (p - torch.from_numpy(lr)[:, None, None, None] * torch.nan_to_num(gp.cpu()).sign()).clamp(0, 1)
+    assert torch.equal(pd.cpu(), pref)
+    if stage == 0:
+        nan_ref = torch.isnan(o["grad_mask"])
+        assert nan_ref[0, 0, :7, :7].all()
+        assert torch.isnan(gm.cpu())[nan_ref].all()                       # NaN reproduced ...
+        assert torch.equal(md.cpu()[nan_ref], m[nan_ref])                 # ... and those pixels frozen
+        check_grad("grad_mask", gm, o["grad_mask"])
+        mref = (m - torch.from_numpy(lr)[:, None, None, None] * torch.nan_to_num(gm.cpu()).sign()).clamp(0, 1)
+        assert torch.equal(md.cpu(), mref)
+    else:
+        assert torch.equal(md.cpu(), m)
+
+
+def test_window_sum(engine_factory):
+    H = 112
+    e = engine_factory(img=H, precision="fp32", chunk=8, max_images=4)
+    m = _rand((2, 1, H, H), 41)
+    got = e.window_sum(m.to(DEV), 7)
+    ref = OA.window_sum(m, 7).reshape(2, -1).numpy()
+    assert np.allclose(got, ref, rtol=1e-5)
