@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- EOT-samples/sec of the DorPatch hot loop (BASELINE.json metric).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl native|reference]
+
+A "step" is one iteration of attack.py:184-342 of the reference over one batch: sample occlusion
+masks on the host, paste + expand (K1), ResNetV2-50x1-BiT forward + backward-to-input (K2),
+CW loss (K4), masked EOT gradient reduce (K1^T), [all-reduce across ranks], host bookkeeping,
+sign step (K3).  Workload = BASELINE.json configs[1]: 32 synthetic 224x224 images x 16 EOT
+occlusion samples per GPU and step, 5 % patch budget (stage-1 step on a selected binary mask),
+untargeted, double-mask universe (2520).  Weak scaling: every GPU always processes 32 x 16
+samples, so the per-image EOT count is 16 x N.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = the same step
+through host buffers (H2D of x/mask/pattern + D2H of mask/pattern/losses every step),
+`roofline` = the hand-written K1 expand kernel against measured HBM copy bandwidth,
+`kernels` = per-category device time / achieved rate of one profiled step,
+`cpu_baseline` = the oracle port of the reference's step timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMG, B_PER_GPU, S_PER_GPU = 224, 32, 16
+GFLOP_PER_SAMPLE = 16.36        # 8.18 fwd + 8.18 dgrad
+METRIC, UNIT = "EOT-samples/sec", "samples/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].startswith("Active") for r in self.rows)]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's step on host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_step_factory(S):
+    import torch
+    from oracle import attack as OA, masks as OM, resnetv2 as OR
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = OR.random_init(seed=0)
+    net = OR.OracleNet(params, weights_require_grad=True).eval()     # the reference never freezes the weights (Q7)
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(1, 3, IMG, IMG, generator=g)
+    pattern = torch.rand(1, 3, IMG, IMG, generator=g)
+    imp = torch.rand(1, 1, IMG, IMG, generator=g)
+    mask = OA.patch_selection(imp, 0.05)
+    uni = torch.from_numpy(OM.rects_to_bool(OM.universe_rects(IMG, 2), IMG))
+    lvx = OA.local_variance(x)[0].mean(1)
+    with torch.no_grad():
+        y = net(x).argmax(-1)
+    rng = np.random.RandomState(0)
+    state = dict(pattern=pattern)
+
+    def step():
+        idx = rng.choice(np.arange(uni.shape[0]), S, replace=False)[None]
+        r = OA.step_losses_and_grads(net, x, mask, state["pattern"], y, idx, uni, [False], 1000, 0.1, [1e-3], 1e-3,
+                                     [1e-5], 1, 4.0, lvx)
+        state["pattern"] = (state["pattern"] - 0.01 * r["grad_pattern"].sign()).clamp(0, 1)
+        return S
+    return step, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, threads = cpu_step_factory(S_PER_GPU)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(args.steps):
+        n += step()
+    dt = time.perf_counter() - t0
+    v = n / dt
+    sample = "1 image x %d EOT occlusion samples per step (same per-image work; B scaled 32->1), stage-1 step, fp32, weights requires_grad as the reference" % S_PER_GPU
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n_gpus):
+    return {"workload": "configs[1]: batch 32 x 16 EOT per GPU, 224x224, ResNetV2-50x1-BiT random-init, 5% patch budget, "
+                        "untargeted, stage-1 step, double-mask universe (2520)",
+            "images_per_gpu": B_PER_GPU, "eot_per_image_per_gpu": S_PER_GPU, "eot_per_image_total": S_PER_GPU * n_gpus,
+            "img": IMG, "parallelism": "eot-shard x%d + 1 allreduce(patch grad)/step" % n_gpus,
+            "l2_policy": "inputs larger than L2 (>= 150 MB network input + ~15 GB activations per step)"}
+
+
+# ----------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from dorpatch_b200 import masks as PM
+    from dorpatch_b200.attack import DorPatch, _ImageState
+    from dorpatch_b200.engine import Engine
+    from dorpatch_b200.resnetv2 import ResNetV2
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, (world, args.gpus)
+
+    B, S_loc = args.batch, args.eot
+    S = S_loc * world
+    pk = peaks()
+    eng = Engine(img=IMG, precision=args.precision, chunk=args.chunk, max_images=B, device=local, autotune=True)
+    net = ResNetV2(seed=0)
+    eng.load_state_dict(net.state_dict())
+
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(B, 3, IMG, IMG, generator=g).to(dev)
+    pattern = torch.rand(B, 3, IMG, IMG, generator=g).to(dev)
+    importance = torch.rand(B, 1, IMG, IMG, generator=g).to(dev)
+    mask = DorPatch().patch_selection(importance, 0.05)                 # 5 % budget binary mask (stage 1)
+    G = torch.zeros_like(x)
+    table = PM.universe(IMG, 2)
+    n_mask = table.shape[0]
+    y = eng.predict(x).astype(np.int64)
+    np.random.seed(1234)
+    states = [_ImageState(0.01, 1e-3, y[b], False, np.random.RandomState(1234 + b)) for b in range(B)]
+    stage = 1
+
+    def host_sample(i):
+        idx = np.stack([s.sample(i, n_mask, S)[0] for s in states])
+        return idx, PM.gather(table, idx[:, rank * S_loc:(rank + 1) * S_loc])
+
+    def finish(i, idx, r):
+        loss_adv = r["loss_adv"]
+        if world > 1:
+            dist.all_reduce(G)
+            pack = torch.from_numpy(loss_adv).to(dev)
+            outs = [torch.empty_like(pack) for _ in range(world)]
+            dist.all_gather(outs, pack)
+            loss_adv = np.concatenate([o.cpu().numpy() for o in outs], 1)
+        lr = np.zeros(B, np.float32)
+        st_used = [s.structured for s in states]
+        for b, s in enumerate(states):
+            s.bookkeeping(stage, i, loss_adv[b], idx[b], 0, r["loss_struc"][b])
+            lr[b] = 0.01
+        return lr, st_used
+
+    def step(i):
+        idx, rects = host_sample(i)
+        r = eng.attack_grad(x, mask, pattern, rects, y, [False] * B, 0.1, 4.0, stage, G, S_total=S)
+        lr, st_used = finish(i, idx, r)
+        eng.attack_update(x, mask, pattern, G, lr, st_used, None, 1e-3, stage)
+
+    # pinned host mirrors for the end-to-end leg
+    hx = torch.empty(x.shape, pin_memory=True).copy_(x)
+    hm = torch.empty(mask.shape, pin_memory=True).copy_(mask)
+    hp = torch.empty(pattern.shape, pin_memory=True).copy_(pattern)
+    dx, dm, dp_ = torch.empty_like(x), torch.empty_like(mask), torch.empty_like(pattern)
+
+    def step_e2e(i):
+        idx, rects = host_sample(i)
+        if world == 1:
+            lr = np.full(B, 0.01, np.float32)
+            st_used = [s.structured for s in states]
+            r = eng.attack_step_host(hx.numpy(), hm.numpy(), hp.numpy(), rects, y, [False] * B, 0.1, 4.0, stage, lr,
+                                     st_used, None, 1e-3, S_total=S)
+            for b, s in enumerate(states):
+                s.bookkeeping(stage, i, r["loss_adv"][b], idx[b], 0, r["loss_struc"][b])
+        else:
+            dx.copy_(hx, non_blocking=True); dm.copy_(hm, non_blocking=True); dp_.copy_(hp, non_blocking=True)
+            r = eng.attack_grad(dx, dm, dp_, rects, y, [False] * B, 0.1, 4.0, stage, G, S_total=S)
+            lr, st_used = finish(i, idx, r)
+            eng.attack_update(dx, dm, dp_, G, lr, st_used, None, 1e-3, stage)
+            hm.copy_(dm, non_blocking=True); hp.copy_(dp_, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, K, i0):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count
+        e0.record()
+        for k in range(K):
+            fn(i0 + k)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), eng.launch_count - l0
+
+    W, K = max(args.warmup, 3), args.steps
+    for i in range(W):
+        step(i)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ms, launches = timed(step, K, W)
+    clocks = sampler.stop()
+    for i in range(2):
+        step_e2e(W + K + i)
+    ms_e2e, _ = timed(step_e2e, K, W + K + 2)
+    N_step = B * S_loc * world
+    value = N_step * K / (ms / 1e3)
+    e2e_value = N_step * K / (ms_e2e / 1e3)
+    es = eng.elem_bytes
+    h2d = B * 7 * IMG * IMG * 4 + B * S_loc * 32 + B * S_loc * 5
+    d2h = B * 4 * IMG * IMG * 4 + B * S_loc * 8 + B * 16
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic", "config": workload_config(world),
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h),
+                "path": "dp_attack_step_host (C ABI, host buffers)" if world == 1 else "pinned host -> H2D -> grad/allreduce/update -> D2H"},
+        "engine": {"chunk": args.chunk, "c_pad": eng.c_pad, "device_bytes": eng.device_bytes},
+    }
+
+    if rank == 0:
+        # ---- K1 roofline: the hand-written expand kernel alone on the whole step batch -------------
+        Nk = B * S_loc
+        rects_all = PM.gather(table, np.stack([np.random.RandomState(b).choice(n_mask, S_loc, replace=False) for b in range(B)]))
+        eng.expand(x, S_loc, rects_all)                                       # warm-up + allocation
+        torch.cuda.synchronize()
+        buf = torch.empty((Nk, IMG, IMG, eng.c_pad), dtype=torch.bfloat16 if es == 2 else torch.float32, device=dev)
+        import ctypes as C
+        from dorpatch_b200 import _lib
+        ra = np.ascontiguousarray(rects_all.reshape(Nk, 4, 4), np.int16)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        for _ in range(3):
+            _lib.check(eng.lib.dp_expand(eng.handle, C.c_void_p(x.data_ptr()), B, S_loc, C.c_void_p(ra.ctypes.data), C.c_void_p(buf.data_ptr()), eng._stream()))
+        torch.cuda.synchronize()
+        tk = []
+        for _ in range(reps):
+            e0.record()
+            _lib.check(eng.lib.dp_expand(eng.handle, C.c_void_p(x.data_ptr()), B, S_loc, C.c_void_p(ra.ctypes.data), C.c_void_p(buf.data_ptr()), eng._stream()))
+            e1.record()
+            torch.cuda.synchronize()
+            tk.append(e0.elapsed_time(e1))
+        k1_ms = float(np.median(tk))
+        alg_bytes = Nk * IMG * IMG * 3 * es + B * 3 * IMG * IMG * 4
+        act_bytes = Nk * IMG * IMG * eng.c_pad * es + B * 3 * IMG * IMG * 4
+        out["roofline"] = {"kernel": "expand_kernel (K1: paste/normalise/occlude, TMA bulk tiles)", "bound": "hbm",
+                           "achieved": alg_bytes / k1_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
+                           "frac": alg_bytes / k1_ms / 1e6 / pk["hbm"], "traffic": None,
+                           "achieved_incl_channel_pad": act_bytes / k1_ms / 1e6, "ms": k1_ms,
+                           "algorithmic_bytes_per_launch": alg_bytes, "peak_source": pk["src"]}
+        # ---- whole-step tensor roofline + per-category breakdown of one profiled step -------------------
+        out["roofline_step"] = {"bound": "tensor", "achieved": GFLOP_PER_SAMPLE * value / world / 1e3, "peak": pk["tf_sus"],
+                                "unit": "TFLOP/s", "frac": GFLOP_PER_SAMPLE * value / world / 1e3 / pk["tf_sus"],
+                                "note": "16.36 GFLOP (fwd+dgrad) per EOT sample x per-GPU samples/s vs sustained bf16 cuBLAS peak"}
+    # profiled step (all ranks execute it to keep collectives matched)
+    eng.profile(True, reset=True)
+    step(W + 2 * K + 10)
+    torch.cuda.synchronize()
+    prof = eng.profile_read()
+    eng.profile(False)
+    if rank == 0:
+        tot = sum(v["ms"] for v in prof.values()) or 1.0
+        kern = {}
+        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+            d = {"ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 4), "launch_groups": v["count"]}
+            if v["flops"] > 0 and ("conv" in k or "gemm" in k):
+                d["tflops"] = round(v["flops"] / v["ms"] / 1e9, 1)
+                d["frac_of_bf16_peak"] = round(v["flops"] / v["ms"] / 1e9 / pk["tf_burst"], 3)
+            else:
+                d["gbs_algorithmic"] = round(v["bytes"] / v["ms"] / 1e6, 1)
+                d["frac_of_hbm_peak"] = round(v["bytes"] / v["ms"] / 1e6 / pk["hbm"], 3)
+            kern[k] = d
+        out["kernels"] = kern
+        out["kernels_total_ms"] = round(tot, 3)
+        # ---- CPU baseline: oracle port on this box's host cores, bounded sample ----------------------------
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cstep, threads = cpu_step_factory(S_PER_GPU)
+                cstep()
+                t0, n = time.perf_counter(), 0
+                while time.perf_counter() - t0 < args.cpu_seconds:
+                    n += cstep()
+                dt = time.perf_counter() - t0
+                out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                       "sample": "%d steps of 1 image x %d EOT samples (%.1f s), stage-1 step, fp32 torch-CPU oracle port, weight grads on as in the reference" % (n // S_PER_GPU, S_PER_GPU, dt)}
+            except Exception as ex:   # the bench line must survive a CPU-side problem
+                out["cpu_baseline"] = {"error": repr(ex)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("DORPATCH_PRECISION", "bf16"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("DORPATCH_CHUNK", "128")))
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--eot", type=int, default=S_PER_GPU)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -45,6 +45,8 @@ SIGNATURES = {
     "dp_engine_load_weights": (c_i32, [c_vp, c_i32, C.POINTER(C.c_char_p), C.POINTER(c_vp), C.POINTER(c_i64)]),
     "dp_engine_device_bytes": (c_i64, [c_vp]),
     "dp_engine_launch_count": (c_i64, [c_vp]),
+    "dp_engine_profile": (c_i32, [c_vp, c_i32]),
+    "dp_engine_profile_read": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, C.POINTER(c_i32)]),
     "dp_paste": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "dp_window_sum": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "dp_expand": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),

@@ -56,6 +56,9 @@ thread_local std::string g_last_error;
     if (_s != CUBLAS_STATUS_SUCCESS) fail("cuBLASLt error %d at %s:%d [%s]", (int)_s, __FILE__, __LINE__, #expr); \
   } while (0)
 #define KERNEL_OK() CUDA_OK(cudaGetLastError())
+// PROF(engine, "category", algorithmic bytes, flops, stream, statement)
+#define PROF(E, NAME, BYTES, FLOPS, ST, ...) \
+  do { (E)->prof_begin(NAME, (double)(BYTES), (double)(FLOPS), ST); __VA_ARGS__; (E)->prof_end(ST); } while (0)
 
 constexpr int DEPTHS[4] = {3, 4, 6, 3};
 constexpr int WIDTHS[4] = {256, 512, 1024, 2048};
@@ -140,6 +143,43 @@ struct dp_engine {
   float* loss_d = nullptr; int32_t* preds_d = nullptr;
   // pinned staging
   unsigned char* pin = nullptr; size_t pin_bytes = 0;
+
+  // ---- optional per-category profiler (CUDA events around every launch) --------------
+  bool prof_on = false;
+  struct ProfRec { int cat; cudaEvent_t a, b; double bytes, flops; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  std::vector<std::string> prof_names;
+  std::vector<double> prof_ms, prof_bytes, prof_flops;
+  std::vector<int64_t> prof_count;
+  int prof_cat(const char* name) {
+    for (size_t i = 0; i < prof_names.size(); ++i) if (prof_names[i] == name) return (int)i;
+    prof_names.push_back(name); prof_ms.push_back(0); prof_bytes.push_back(0); prof_flops.push_back(0); prof_count.push_back(0);
+    return (int)prof_names.size() - 1;
+  }
+  cudaEvent_t prof_event() {
+    if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+    cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); return e;
+  }
+  void prof_begin(const char* name, double bytes, double flops, cudaStream_t st) {
+    if (!prof_on) return;
+    ProfRec r; r.cat = prof_cat(name); r.bytes = bytes; r.flops = flops; r.a = prof_event(); r.b = prof_event();
+    CUDA_OK(cudaEventRecord(r.a, st));
+    prof_recs.push_back(r);
+  }
+  void prof_end(cudaStream_t st) {
+    if (!prof_on) return;
+    CUDA_OK(cudaEventRecord(prof_recs.back().b, st));
+  }
+  void prof_collect() {
+    for (auto& r : prof_recs) {
+      CUDA_OK(cudaEventSynchronize(r.b));
+      float ms = 0.f; CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
+      prof_ms[r.cat] += ms; prof_bytes[r.cat] += r.bytes; prof_flops[r.cat] += r.flops; prof_count[r.cat] += 1;
+      prof_pool.push_back(r.a); prof_pool.push_back(r.b);
+    }
+    prof_recs.clear();
+  }
 
   std::map<std::pair<int, int>, CudnnPlan> cudnn_plans;                 // (layer id, N)
   std::map<std::tuple<int, int, int, int>, GemmPlan> gemm_plans;        // (rows, n_out, k, mode)
@@ -385,7 +425,10 @@ struct dp_engine {
     if (!p.fwd_ready) pick_fwd(p, c, x, y);
     CUDNN_OK(cudnnSetConvolutionMathType(c.cdesc, p.fwd_math));
     const float one = 1.f, zero = 0.f;
-    CUDNN_OK(cudnnConvolutionForward(cudnn, &one, p.xdesc, x, c.wdesc, c.w, c.cdesc, p.fwd_algo, lib_ws, lib_ws_bytes, &zero, p.ydesc, y));
+    const double fl = 2.0 * N * hout * hout * c.cout * c.k * c.k * c.cin;
+    const double by = ((double)N * hin * hin * c.cin_pad + (double)N * hout * hout * c.cout + (double)c.cout * c.k * c.k * c.cin_pad) * es;
+    PROF(this, c.k == 7 ? "stem_conv_fwd" : "conv3x3_fwd", by, fl, st,
+         CUDNN_OK(cudnnConvolutionForward(cudnn, &one, p.xdesc, x, c.wdesc, c.w, c.cdesc, p.fwd_algo, lib_ws, lib_ws_bytes, &zero, p.ydesc, y)));
     ++launches;
   }
   void conv_bwd(int layer_id, const ConvW& c, int N, int hin, int hout, const void* dy, void* dx, cudaStream_t st) {
@@ -393,7 +436,10 @@ struct dp_engine {
     if (!p.bwd_ready) pick_bwd(p, c, dy, dx);
     CUDNN_OK(cudnnSetConvolutionMathType(c.cdesc, p.bwd_math));
     const float one = 1.f, zero = 0.f;
-    CUDNN_OK(cudnnConvolutionBackwardData(cudnn, &one, c.wdesc, c.w, p.ydesc, dy, c.cdesc, p.bwd_algo, lib_ws, lib_ws_bytes, &zero, p.xdesc, dx));
+    const double fl = 2.0 * N * hout * hout * c.cout * c.k * c.k * c.cin;
+    const double by = ((double)N * hin * hin * c.cin_pad + (double)N * hout * hout * c.cout + (double)c.cout * c.k * c.k * c.cin_pad) * es;
+    PROF(this, c.k == 7 ? "stem_conv_bwd" : "conv3x3_bwd", by, fl, st,
+         CUDNN_OK(cudnnConvolutionBackwardData(cudnn, &one, c.wdesc, c.w, p.ydesc, dy, c.cdesc, p.bwd_algo, lib_ws, lib_ws_bytes, &zero, p.xdesc, dx)));
     ++launches;
   }
 
@@ -428,7 +474,9 @@ struct dp_engine {
   void gemm(int rows, int nout, int k, int mode, const void* W, const void* X, const void* Cres, float beta, void* D, cudaStream_t st) {
     GemmPlan& p = gemm_plan(rows, nout, k, mode);
     const float one = 1.f;
-    CUBLAS_OK(cublasLtMatmul(lt, p.op, &one, W, p.a, X, p.b, &beta, Cres ? Cres : D, p.c, D, p.c, &p.algo, lib_ws, lib_ws_bytes, st));
+    const double by = ((double)rows * k + (double)rows * nout * (beta != 0.f ? 2 : 1) + (double)nout * k) * es;
+    PROF(this, mode == 0 ? "gemm1x1_fwd" : "gemm1x1_bwd", by, 2.0 * rows * nout * k, st,
+         CUBLAS_OK(cublasLtMatmul(lt, p.op, &one, W, p.a, X, p.b, &beta, Cres ? Cres : D, p.c, D, p.c, &p.algo, lib_ws, lib_ws_bytes, st)));
     ++launches;
   }
 
@@ -440,33 +488,42 @@ struct dp_engine {
     CUDNN_OK(cudnnSetStream(cudnn, st));
     const int hs = Hs(), hp = Hp();
     conv_fwd(0, stem, N, H, hs, input, act, st);
-    dp::launch_maxpool_forward(act, x0, train ? pool_amax : nullptr, N, hs, hs, STEM_CH, bf16, st); KERNEL_OK(); ++launches;
+    PROF(this, "maxpool_fwd", (double)N * (hs * hs + hp * hp) * STEM_CH * es, 0, st,
+         dp::launch_maxpool_forward(act, x0, train ? pool_amax : nullptr, N, hs, hs, STEM_CH, bf16, st)); KERNEL_OK(); ++launches;
     const void* cur = x0;
     int lid = 1;
     for (auto& b : blocks) {
       const int pin_ = b.hin * b.hin, pout = b.hout * b.hout;
       // xp = relu(gn1(cur))
-      dp::launch_gn_relu_forward(cur, act, b.n1.gamma, b.n1.beta, gn_partial, b.st1, N, pin_, b.cin, bf16, st); KERNEL_OK(); launches += 2;
+      PROF(this, "gn_relu_fwd", 2.0 * N * pin_ * b.cin * es, 0, st,
+           dp::launch_gn_relu_forward(cur, act, b.n1.gamma, b.n1.beta, gn_partial, b.st1, N, pin_, b.cin, bf16, st)); KERNEL_OK(); launches += 2;
       const void* shortcut = cur;
       if (b.has_ds) {
         const void* src = act;
-        if (b.stride == 2) { dp::launch_subsample2(act, act2, N, b.hin, b.hin, b.cin, bf16, st); KERNEL_OK(); ++launches; src = act2; }
+        if (b.stride == 2) {
+          PROF(this, "subsample", 2.0 * N * pout * b.cin * es, 0, st, dp::launch_subsample2(act, act2, N, b.hin, b.hin, b.cin, bf16, st));
+          KERNEL_OK(); ++launches; src = act2;
+        }
         gemm(N * pout, b.cout, b.cin, 0, b.ds.w, src, nullptr, 0.f, b.out, st);
         shortcut = b.out;
       }
       gemm(N * pin_, b.mid, b.cin, 0, b.c1.w, act, nullptr, 0.f, b.h1, st);
-      dp::launch_gn_relu_forward(b.h1, act, b.n2.gamma, b.n2.beta, gn_partial, b.st2, N, pin_, b.mid, bf16, st); KERNEL_OK(); launches += 2;
+      PROF(this, "gn_relu_fwd", 2.0 * N * pin_ * b.mid * es, 0, st,
+           dp::launch_gn_relu_forward(b.h1, act, b.n2.gamma, b.n2.beta, gn_partial, b.st2, N, pin_, b.mid, bf16, st)); KERNEL_OK(); launches += 2;
       conv_fwd(lid, b.c2, N, b.hin, b.hout, act, b.h2, st);
-      dp::launch_gn_relu_forward(b.h2, act, b.n3.gamma, b.n3.beta, gn_partial, b.st3, N, pout, b.mid, bf16, st); KERNEL_OK(); launches += 2;
+      PROF(this, "gn_relu_fwd", 2.0 * N * pout * b.mid * es, 0, st,
+           dp::launch_gn_relu_forward(b.h2, act, b.n3.gamma, b.n3.beta, gn_partial, b.st3, N, pout, b.mid, bf16, st)); KERNEL_OK(); launches += 2;
       gemm(N * pout, b.cout, b.mid, 0, b.c3.w, act, shortcut, 1.f, b.out, st);   // + shortcut fused as C operand
       cur = b.out;
       ++lid;
     }
     const Block& last = blocks.back();
     const int pl = last.hout * last.hout;
-    dp::launch_gn_stats(cur, gn_partial, head_stats, N, pl, last.cout, bf16, st); KERNEL_OK(); launches += 2;
-    dp::launch_head_pool(cur, head_gn.gamma, head_gn.beta, head_stats, pooled, N, pl, last.cout, bf16, st); KERNEL_OK(); ++launches;
-    dp::launch_fc_forward(pooled, fc_w, fc_b, logits, N, last.cout, K, st); KERNEL_OK(); ++launches;
+    PROF(this, "head_fwd", (double)N * pl * last.cout * es, 2.0 * N * last.cout * K, st, {
+      dp::launch_gn_stats(cur, gn_partial, head_stats, N, pl, last.cout, bf16, st);
+      dp::launch_head_pool(cur, head_gn.gamma, head_gn.beta, head_stats, pooled, N, pl, last.cout, bf16, st);
+      dp::launch_fc_forward(pooled, fc_w, fc_b, logits, N, last.cout, K, st);
+    }); KERNEL_OK(); launches += 4;
   }
 
   // ---- classifier backward (to the input) -----------------------------------------------------
@@ -476,9 +533,11 @@ struct dp_engine {
     const Block& last = blocks.back();
     const int pl = last.hout * last.hout;
     void *GA = g[0], *GB = g[1], *GC = g[2], *GD = g[3];
-    dp::launch_fc_backward(dlog, fc_w, dpooled, N, last.cout, K, st); KERNEL_OK(); ++launches;
-    dp::launch_pool_grad_bcast(dpooled, GB, N, pl, last.cout, bf16, st); KERNEL_OK(); ++launches;
-    dp::launch_gn_relu_backward(GB, last.out, nullptr, GA, head_gn.gamma, head_gn.beta, head_stats, gn_partial, N, pl, last.cout, bf16, st); KERNEL_OK(); launches += 2;
+    PROF(this, "head_bwd", 2.0 * N * pl * last.cout * es, 2.0 * N * last.cout * K, st, {
+      dp::launch_fc_backward(dlog, fc_w, dpooled, N, last.cout, K, st);
+      dp::launch_pool_grad_bcast(dpooled, GB, N, pl, last.cout, bf16, st);
+      dp::launch_gn_relu_backward(GB, last.out, nullptr, GA, head_gn.gamma, head_gn.beta, head_stats, gn_partial, N, pl, last.cout, bf16, st);
+    }); KERNEL_OK(); launches += 4;
     for (int bi = (int)blocks.size() - 1; bi >= 0; --bi) {
       Block& b = blocks[bi];
       const int lid = bi + 1;
@@ -486,25 +545,30 @@ struct dp_engine {
       const void* xin = (bi == 0) ? x0 : blocks[bi - 1].out;
       // d_a3 = d_out * W3
       gemm(N * pout, b.mid, b.cout, 1, b.c3.w, GA, nullptr, 0.f, GB, st);
-      dp::launch_gn_relu_backward(GB, b.h2, nullptr, GC, b.n3.gamma, b.n3.beta, b.st3, gn_partial, N, pout, b.mid, bf16, st); KERNEL_OK(); launches += 2;
+      PROF(this, "gn_relu_bwd", 3.0 * N * pout * b.mid * es, 0, st,
+           dp::launch_gn_relu_backward(GB, b.h2, nullptr, GC, b.n3.gamma, b.n3.beta, b.st3, gn_partial, N, pout, b.mid, bf16, st)); KERNEL_OK(); launches += 2;
       conv_bwd(lid, b.c2, N, b.hin, b.hout, GC, GB, st);
-      dp::launch_gn_relu_backward(GB, b.h1, nullptr, GC, b.n2.gamma, b.n2.beta, b.st2, gn_partial, N, pin_, b.mid, bf16, st); KERNEL_OK(); launches += 2;
+      PROF(this, "gn_relu_bwd", 3.0 * N * pin_ * b.mid * es, 0, st,
+           dp::launch_gn_relu_backward(GB, b.h1, nullptr, GC, b.n2.gamma, b.n2.beta, b.st2, gn_partial, N, pin_, b.mid, bf16, st)); KERNEL_OK(); launches += 2;
       gemm(N * pin_, b.cin, b.mid, 1, b.c1.w, GC, nullptr, 0.f, GB, st);          // d_xp (conv1 path)
       if (b.has_ds) {
         if (b.stride == 2) {
           gemm(N * pout, b.cin, b.cout, 1, b.ds.w, GA, nullptr, 0.f, GC, st);
-          dp::launch_subsample2_adjoint_add(GC, GB, N, b.hin, b.hin, b.cin, bf16, st); KERNEL_OK(); ++launches;
+          PROF(this, "subsample", 3.0 * N * pout * b.cin * es, 0, st, dp::launch_subsample2_adjoint_add(GC, GB, N, b.hin, b.hin, b.cin, bf16, st)); KERNEL_OK(); ++launches;
         } else {
           gemm(N * pout, b.cin, b.cout, 1, b.ds.w, GA, nullptr, 1.f, GB, st);    // accumulate
         }
-        dp::launch_gn_relu_backward(GB, xin, nullptr, GD, b.n1.gamma, b.n1.beta, b.st1, gn_partial, N, pin_, b.cin, bf16, st); KERNEL_OK(); launches += 2;
+        PROF(this, "gn_relu_bwd", 3.0 * N * pin_ * b.cin * es, 0, st,
+             dp::launch_gn_relu_backward(GB, xin, nullptr, GD, b.n1.gamma, b.n1.beta, b.st1, gn_partial, N, pin_, b.cin, bf16, st)); KERNEL_OK(); launches += 2;
       } else {
-        dp::launch_gn_relu_backward(GB, xin, GA, GD, b.n1.gamma, b.n1.beta, b.st1, gn_partial, N, pin_, b.cin, bf16, st); KERNEL_OK(); launches += 2;
+        PROF(this, "gn_relu_bwd", 4.0 * N * pin_ * b.cin * es, 0, st,
+             dp::launch_gn_relu_backward(GB, xin, GA, GD, b.n1.gamma, b.n1.beta, b.st1, gn_partial, N, pin_, b.cin, bf16, st)); KERNEL_OK(); launches += 2;
       }
       std::swap(GA, GD);
     }
     const int hs = Hs();
-    dp::launch_maxpool_backward(GA, pool_amax, GB, N, hs, hs, STEM_CH, bf16, st); KERNEL_OK(); ++launches;
+    PROF(this, "maxpool_bwd", (double)N * (hs * hs + (hs / 2) * (hs / 2)) * STEM_CH * es, 0, st,
+         dp::launch_maxpool_backward(GA, pool_amax, GB, N, hs, hs, STEM_CH, bf16, st)); KERNEL_OK(); ++launches;
     conv_bwd(0, stem, N, H, hs, GB, GC, st);
     d_input = GC;
   }
@@ -605,6 +669,8 @@ void dp_engine_destroy(dp_engine* e) {
   };
   kill(e->stem);
   for (auto& b : e->blocks) { kill(b.ds); kill(b.c1); kill(b.c2); kill(b.c3); }
+  for (auto& r : e->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   for (void* p : e->allocs) cudaFree(p);
   if (e->pin) cudaFreeHost(e->pin);
   if (e->cudnn) cudnnDestroy(e->cudnn);
@@ -622,6 +688,34 @@ int32_t dp_engine_load_weights(dp_engine* e, int32_t n, const char* const* names
 
 int64_t dp_engine_device_bytes(const dp_engine* e) { return e ? e->device_bytes : 0; }
 int64_t dp_engine_launch_count(const dp_engine* e) { return e ? e->launches : 0; }
+
+int32_t dp_engine_profile(dp_engine* e, int32_t enable) {
+  DP_TRY
+  if (!e) fail("null engine");
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  e->prof_collect();
+  e->prof_on = enable != 0;
+  if (enable == 2) {   // reset
+    for (size_t i = 0; i < e->prof_ms.size(); ++i) { e->prof_ms[i] = 0; e->prof_bytes[i] = 0; e->prof_flops[i] = 0; e->prof_count[i] = 0; }
+  }
+  DP_CATCH
+}
+
+int32_t dp_engine_profile_read(dp_engine* e, int32_t max_n, char* names, int32_t name_stride, double* ms, double* bytes,
+                               double* flops, int64_t* counts, int32_t* n_out) {
+  DP_TRY
+  if (!e) fail("null engine");
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  e->prof_collect();
+  int n = (int)e->prof_names.size();
+  if (n > max_n) n = max_n;
+  for (int i = 0; i < n; ++i) {
+    snprintf(names + (size_t)i * name_stride, name_stride, "%s", e->prof_names[i].c_str());
+    ms[i] = e->prof_ms[i]; bytes[i] = e->prof_bytes[i]; flops[i] = e->prof_flops[i]; counts[i] = e->prof_count[i];
+  }
+  *n_out = n;
+  DP_CATCH
+}
 
 int32_t dp_input_layout(const dp_engine* e, int32_t* c_pad, int32_t* elem_bytes) {
   DP_TRY
@@ -668,8 +762,9 @@ int32_t dp_expand(dp_engine* e, const float* img, int32_t B, int32_t S, const in
   const int N = B * S;
   if (out == nullptr && N > e->chunk) fail("dp_expand: B*S=%d exceeds chunk=%d and no output buffer was given", N, e->chunk);
   e->h2d_samples(rects_host, N, st);
-  dp::launch_expand(img, nullptr, nullptr, nullptr, nullptr, rects_host ? e->rects_d : nullptr, out ? out : e->net_in,
-                    B, S, 0, N, e->H, e->H, e->Cp, e->bf16, false, e->num_sms, st);
+  PROF(e, "expand_k1", (double)N * e->H * e->H * 3 * e->es + 3.0 * e->H * e->H * 4 * (double)B, 0, st,
+       dp::launch_expand(img, nullptr, nullptr, nullptr, nullptr, rects_host ? e->rects_d : nullptr, out ? out : e->net_in,
+                         B, S, 0, N, e->H, e->H, e->Cp, e->bf16, false, e->num_sms, st));
   KERNEL_OK(); ++e->launches;
   DP_CATCH
 }
@@ -685,8 +780,9 @@ int32_t dp_predict(dp_engine* e, const float* img, int32_t B, int32_t S, const i
   e->h2d_samples(rects_host, N, st);
   for (int n0 = 0; n0 < N; n0 += e->chunk) {
     const int n = std::min(e->chunk, N - n0);
-    dp::launch_expand(img, nullptr, nullptr, nullptr, nullptr, rects_host ? e->rects_d : nullptr, e->net_in, B, S, n0, n,
-                      e->H, e->H, e->Cp, e->bf16, false, e->num_sms, st);
+    PROF(e, "expand_k1", (double)n * e->H * e->H * 3 * e->es + 3.0 * e->H * e->H * 4 * (double)n / S, 0, st,
+         dp::launch_expand(img, nullptr, nullptr, nullptr, nullptr, rects_host ? e->rects_d : nullptr, e->net_in, B, S, n0, n,
+                           e->H, e->H, e->Cp, e->bf16, false, e->num_sms, st));
     KERNEL_OK(); ++e->launches;
     e->forward(n, e->net_in, false, st);
     dp::launch_argmax(e->logits, e->preds_d + n0, n, e->K, st); KERNEL_OK(); ++e->launches;
@@ -723,21 +819,25 @@ static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t
   if (rect_bytes) CUDA_OK(cudaMemcpyAsync(e->rects_d, rp, rect_bytes, cudaMemcpyHostToDevice, st));
   const int16_t* rects = rect_bytes ? e->rects_d : nullptr;
 
-  dp::launch_paste(a->x, a->mask, a->pattern, e->adv_x, e->l2, e->scale, B, H, H, a->eps, st); KERNEL_OK(); ++e->launches;
-  dp::launch_struct(e->adv_x, a->x, e->loss_struc, e->dLs, B, H, H, st); KERNEL_OK(); ++e->launches;
+  const double img_bytes = (double)B * H * H * 4;
+  PROF(e, "paste", 10.0 * img_bytes, 0, st, dp::launch_paste(a->x, a->mask, a->pattern, e->adv_x, e->l2, e->scale, B, H, H, a->eps, st)); KERNEL_OK(); ++e->launches;
+  PROF(e, "struct", 9.0 * img_bytes, 0, st, dp::launch_struct(e->adv_x, a->x, e->loss_struc, e->dLs, B, H, H, st)); KERNEL_OK(); ++e->launches;
   if (a->stage == 0) {
-    dp::launch_maskreg(a->mask, e->loss_density, e->group_lasso, e->win_dev, e->grp_ss, B, H, H, UNIT, st); KERNEL_OK(); ++e->launches;
+    PROF(e, "maskreg", img_bytes, 0, st, dp::launch_maskreg(a->mask, e->loss_density, e->group_lasso, e->win_dev, e->grp_ss, B, H, H, UNIT, st)); KERNEL_OK(); ++e->launches;
   }
   const float inv_s = 1.0f / (float)a->S_total;
   for (int n0 = 0; n0 < N; n0 += e->chunk) {
     const int n = std::min(e->chunk, N - n0);
-    dp::launch_expand(nullptr, a->x, a->mask, a->pattern, e->scale, rects, e->net_in, B, S, n0, n, H, H, e->Cp, e->bf16, true, e->num_sms, st);
+    PROF(e, "expand_k1", (double)n * H * H * 3 * e->es + 7.0 * H * H * 4 * (double)n / S, 0, st,
+         dp::launch_expand(nullptr, a->x, a->mask, a->pattern, e->scale, rects, e->net_in, B, S, n0, n, H, H, e->Cp, e->bf16, true, e->num_sms, st));
     KERNEL_OK(); ++e->launches;
     e->forward(n, e->net_in, true, st);
-    dp::launch_cw(e->logits, e->y_d + n0, e->tg_d + n0, a->confidence, inv_s, e->loss_d + n0, e->preds_d + n0, e->dlogits, n, e->K, st);
+    PROF(e, "cw_k4", 2.0 * n * e->K * 4, 0, st,
+         dp::launch_cw(e->logits, e->y_d + n0, e->tg_d + n0, a->confidence, inv_s, e->loss_d + n0, e->preds_d + n0, e->dlogits, n, e->K, st));
     KERNEL_OK(); ++e->launches;
     e->backward(n, e->dlogits, st);
-    dp::launch_reduce(e->d_input, rects, a->grad_adv, B, S, n0, n, H, H, e->Cp, e->bf16, st); KERNEL_OK(); ++e->launches;
+    PROF(e, "reduce_k1t", (double)n * H * H * 3 * e->es + 3.0 * H * H * 4 * (double)n / S, 0, st,
+         dp::launch_reduce(e->d_input, rects, a->grad_adv, B, S, n0, n, H, H, e->Cp, e->bf16, st)); KERNEL_OK(); ++e->launches;
   }
   // results -> host (pinned staging, one sync)
   unsigned char* out = e->pin + d2h_off;
@@ -770,8 +870,9 @@ static void attack_update_impl(dp_engine* e, const dp_update_args* u, cudaStream
   CUDA_OK(cudaMemcpyAsync(e->lr_d, h, (size_t)B * 4, cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemcpyAsync(e->structured_d, h + B, (size_t)B * 4, cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemcpyAsync(e->coeff_d, h + 2 * B, (size_t)B * 4, cudaMemcpyHostToDevice, st));
-  dp::launch_update(u->x, u->mask, u->pattern, u->grad_adv, e->dLs, e->scale, e->win_dev, e->grp_ss, e->lr_d, e->structured_d,
-                    e->coeff_d, u->density, u->clip_min, u->clip_max, u->stage, u->grad_pattern_out, u->grad_mask_out, B, e->H, e->H, UNIT, st);
+  PROF(e, "update_k3", (double)B * e->H * e->H * 4 * (u->stage == 0 ? 15.0 : 13.0), 0, st,
+       dp::launch_update(u->x, u->mask, u->pattern, u->grad_adv, e->dLs, e->scale, e->win_dev, e->grp_ss, e->lr_d, e->structured_d,
+                         e->coeff_d, u->density, u->clip_min, u->clip_max, u->stage, u->grad_pattern_out, u->grad_mask_out, B, e->H, e->H, UNIT, st));
   KERNEL_OK(); ++e->launches;
   CUDA_OK(cudaStreamSynchronize(st));   // `pin` may be reused by the next call
 }

@@ -74,6 +74,26 @@ class Engine:
     def launch_count(self):
         return int(self.lib.dp_engine_launch_count(self.handle))
 
+    def profile(self, enable=True, reset=False):
+        """Per-category CUDA-event profiler of the engine's launches (adds sync overhead)."""
+        _lib.check(self.lib.dp_engine_profile(self.handle, 2 if (enable and reset) else (1 if enable else 0)))
+
+    def profile_read(self):
+        """-> {category: dict(ms, bytes, flops, count)} accumulated since the last reset."""
+        n, stride = 64, 32
+        names = C.create_string_buffer(n * stride)
+        ms, by, fl = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        got = C.c_int32()
+        _lib.check(self.lib.dp_engine_profile_read(self.handle, n, C.cast(names, C.c_void_p), stride, C.cast(ms, C.c_void_p),
+                                                   C.cast(by, C.c_void_p), C.cast(fl, C.c_void_p), C.cast(cnt, C.c_void_p),
+                                                   C.byref(got)))
+        out = {}
+        for i in range(got.value):
+            nm = names.raw[i * stride:(i + 1) * stride].split(b"\0")[0].decode()
+            out[nm] = dict(ms=ms[i], bytes=by[i], flops=fl[i], count=int(cnt[i]))
+        return out
+
     def load_state_dict(self, state_dict):
         """timm-named fp32 tensors of resnetv2_50x1_bit (utils.py:57-62 of the reference)."""
         names, arrs = [], []

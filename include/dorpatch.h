@@ -74,6 +74,14 @@ int64_t dp_engine_device_bytes(const dp_engine* e);
 /* number of CUDA kernels / library launches issued by the engine since create */
 int64_t dp_engine_launch_count(const dp_engine* e);
 
+/* Per-kernel-category profiler: CUDA events around every launch the engine issues.
+ * enable: 0 off, 1 on, 2 on + reset counters.  Read returns accumulated device ms, the
+ * ALGORITHMIC bytes / flops of the launches (what a perfect kernel must move / compute) and
+ * launch counts per category; `names` is a [max_n][name_stride] char array. */
+int32_t dp_engine_profile(dp_engine* e, int32_t enable);
+int32_t dp_engine_profile_read(dp_engine* e, int32_t max_n, char* names, int32_t name_stride, double* ms,
+                               double* bytes, double* flops, int64_t* counts, int32_t* n_out);
+
 /* ---- per-image pieces ----------------------------------------------------------- */
 /* adv_x = x + clip(mask, pattern, x, eps)  (utils.py:105-110, attack.py:185).
  * x, pattern, adv_x_out: [B,3,H,W] fp32 NCHW dev; mask [B,1,H,W] dev;

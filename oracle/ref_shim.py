@@ -20,6 +20,7 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 """
 import contextlib
 import importlib
+import importlib.util
 import os
 import sys
 import types
@@ -52,10 +53,24 @@ def reference_modules():
         torch.Tensor.cpu = lambda self, *a, **k: self.clone()
         torch.nn.Module.cuda = lambda self, *a, **k: self
         ns = types.SimpleNamespace()
-        ns.utils = importlib.import_module("utils")
-        ns.PatchCleanser = importlib.import_module("defenses.PatchCleanser")
-        ns.attack = importlib.import_module("attack")
+        # Load by file path: the repo root holds same-named drop-in modules (attack, utils,
+        # defenses/ -- a regular package, which would shadow the reference's namespace package).
+        pkg = types.ModuleType("defenses")
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "defenses")]
+        sys.modules["defenses"] = pkg
+
+        def load(name, rel):
+            spec = importlib.util.spec_from_file_location(name, os.path.join(REFERENCE_ROOT, rel))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+            return mod
+
+        ns.utils = load("utils", "utils.py")
+        ns.PatchCleanser = load("defenses.PatchCleanser", "defenses/PatchCleanser.py")
+        ns.attack = load("attack", "attack.py")
         assert ns.attack.__file__.startswith(REFERENCE_ROOT), ns.attack.__file__
+        assert ns.attack.MaskWindow is ns.PatchCleanser.MaskWindow and ns.attack.clip is ns.utils.clip
         yield ns
     finally:
         torch.Tensor.cuda, torch.Tensor.cpu, torch.nn.Module.cuda = t_cuda, t_cpu, m_cuda
