@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdorpatch.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
@@ -33,7 +33,7 @@ class DpUpdateArgs(C.Structure):
                 ("x", c_vp), ("mask", c_vp), ("pattern", c_vp), ("grad_adv", c_vp),
                 ("lr_host", c_vp), ("structured_host", c_vp), ("coeff_gl_host", c_vp),
                 ("density", c_f32), ("clip_min", c_f32), ("clip_max", c_f32),
-                ("grad_pattern_out", c_vp), ("grad_mask_out", c_vp)]
+                ("grad_pattern_out", c_vp), ("grad_mask_out", c_vp), ("grad_pattern_bias", c_vp)]
 
 
 # name -> (restype, argtypes); every symbol include/dorpatch.h declares

@@ -153,6 +153,22 @@ def _dist():
     return None
 
 
+def exchange_shards(dist, G, loss_adv, preds):
+    """The only cross-rank exchange of a step: SUM all-reduce of the patch gradient G
+    [B,3,H,W] (each rank holds the sum over ITS S/world samples, already divided by the global
+    S) and an all-gather of the per-sample results [B,S/world] -> [B,S] in rank order, so every
+    rank takes the identical bookkeeping decisions and the identical sign step."""
+    world = dist.get_world_size()
+    dist.all_reduce(G)
+    pack = torch.from_numpy(np.concatenate([loss_adv, preds.astype(np.float32)], 1)).to(G.device)
+    outs = [torch.empty_like(pack) for _ in range(world)]
+    dist.all_gather(outs, pack)
+    s_loc = loss_adv.shape[1]
+    loss_all = np.concatenate([o[:, :s_loc].cpu().numpy() for o in outs], 1)
+    preds_all = np.concatenate([o[:, s_loc:].cpu().numpy() for o in outs], 1).astype(np.int32)
+    return loss_all, preds_all
+
+
 class DorPatch(object):
     def __init__(self):
         self.last_stats = {}
@@ -205,6 +221,11 @@ class DorPatch(object):
         st = [_ImageState(lr, structured, y[b], targeted, rngs[b]) for b in range(B)]
         dir_0 = os.path.dirname(save_dir.rstrip('/')) if save_dir else None
         G = torch.zeros_like(x)
+        # Reference quirk: an early-stop `break` in stage 0 (attack.py:310-315) skips
+        # `adv_pattern.grad.zero_()` (:342), so the first stage-1 backward accumulates onto the
+        # gradient of the last stage-0 iteration.  Kept per image, zero unless stage 0 stopped early.
+        stale_gp = torch.zeros_like(x)
+        have_stale = False
         last_preds = None
         steps = 0
 
@@ -276,19 +297,17 @@ class DorPatch(object):
                                     [s.crit_targeted for s in st], confidence, eps, stage, G, S_total=S)
                 loss_adv, preds = r["loss_adv"], r["preds"]
                 if dist:                                         # one all-reduce of the patch gradient per step
-                    dist.all_reduce(G)
-                    pack = torch.from_numpy(np.concatenate([loss_adv, preds.astype(np.float32)], 1)).to(dev)
-                    outs = [torch.empty_like(pack) for _ in range(world)]
-                    dist.all_gather(outs, pack)
-                    loss_adv = np.concatenate([o[:, :S_loc].cpu().numpy() for o in outs], 1)
-                    preds = np.concatenate([o[:, S_loc:].cpu().numpy() for o in outs], 1).astype(np.int32)
+                    loss_adv, preds = exchange_shards(dist, G, loss_adv, preds)
                 last_preds = preds
                 loss_target = r["group_lasso"] if stage == 0 else r["loss_struc"]
                 lr_used = np.zeros(B, np.float32)
+                stopped_now = []
                 for b, s in enumerate(st):
                     if not s.active:
                         continue
                     improved, stop = s.bookkeeping(stage, i, loss_adv[b], idx[b], nff[b], loss_target[b])
+                    if stop:
+                        stopped_now.append(b)
                     if improved:                                 # best snapshot stays on the device
                         if stage == 0:
                             mask_best[b].copy_(adv_mask[b])
@@ -302,6 +321,13 @@ class DorPatch(object):
                     else:
                         lr_used[b] = s.lr
                 steps += 1
+                if stage == 0 and stopped_now:                   # capture the gradient the reference leaves in .grad
+                    gp_full = torch.empty_like(x)
+                    eng.attack_update(x, adv_mask, adv_pattern, G, np.zeros(B, np.float32), structured_used, coeff_used,
+                                      density, stage, clip_min, clip_max, grad_pattern_out=gp_full)
+                    for b in stopped_now:
+                        stale_gp[b].copy_(gp_full[b])
+                    have_stale = True
                 if not any(s.active for s in st):
                     break
                 if i % 20 == 0:                                  # attack.py:317-330
@@ -319,8 +345,9 @@ class DorPatch(object):
                         msg += ", group lasso: {:.2f}, density: {:.2f}".format(
                             float(r["group_lasso"].mean()), float(r["loss_density"].mean()))
                     print(msg)
+                bias = stale_gp if (stage == 1 and i == 0 and have_stale) else None
                 eng.attack_update(x, adv_mask, adv_pattern, G, lr_used, structured_used, coeff_used, density, stage,
-                                  clip_min, clip_max)            # attack.py:332-342
+                                  clip_min, clip_max, grad_pattern_bias=bias)   # attack.py:332-342
             for b, s in enumerate(st):                           # attack.py:344-346
                 if s.active and np.isinf(s.loss_best):
                     mask_best[b].copy_(adv_mask[b])

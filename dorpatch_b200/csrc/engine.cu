@@ -872,7 +872,7 @@ static void attack_update_impl(dp_engine* e, const dp_update_args* u, cudaStream
   CUDA_OK(cudaMemcpyAsync(e->coeff_d, h + 2 * B, (size_t)B * 4, cudaMemcpyHostToDevice, st));
   PROF(e, "update_k3", (double)B * e->H * e->H * 4 * (u->stage == 0 ? 15.0 : 13.0), 0, st,
        dp::launch_update(u->x, u->mask, u->pattern, u->grad_adv, e->dLs, e->scale, e->win_dev, e->grp_ss, e->lr_d, e->structured_d,
-                         e->coeff_d, u->density, u->clip_min, u->clip_max, u->stage, u->grad_pattern_out, u->grad_mask_out, B, e->H, e->H, UNIT, st));
+                         e->coeff_d, u->density, u->clip_min, u->clip_max, u->stage, u->grad_pattern_out, u->grad_mask_out, u->grad_pattern_bias, B, e->H, e->H, UNIT, st));
   KERNEL_OK(); ++e->launches;
   CUDA_OK(cudaStreamSynchronize(st));   // `pin` may be reused by the next call
 }
@@ -909,7 +909,7 @@ int32_t dp_attack_step_host(dp_engine* e, const dp_attack_args* g, const dp_upda
   attack_grad_impl(e, &ga, st);
   dp_update_args ua = *u;
   ua.x = e->host_x; ua.mask = e->host_mask; ua.pattern = e->host_pattern; ua.grad_adv = e->host_G;
-  ua.grad_pattern_out = nullptr; ua.grad_mask_out = nullptr;
+  ua.grad_pattern_out = nullptr; ua.grad_mask_out = nullptr; ua.grad_pattern_bias = nullptr;
   attack_update_impl(e, &ua, st);
   CUDA_OK(cudaMemcpyAsync(u->mask, e->host_mask, B * HW * 4, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaMemcpyAsync(u->pattern, e->host_pattern, B * 3 * HW * 4, cudaMemcpyDeviceToHost, st));

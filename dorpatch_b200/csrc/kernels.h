@@ -72,7 +72,7 @@ void launch_maskreg(const float* mask, float* loss_density, float* group_lasso, 
 void launch_update(const float* x, float* mask, float* pattern, const float* G, const float* dLs,
                    const float* scale, const float* win_dev, const float* grp_ss, const float* lr,
                    const float* structured, const float* coeff_gl, float density, float lo, float hi, int stage,
-                   float* gp_out, float* gm_out, int B, int H, int W, int unit, cudaStream_t st);
+                   float* gp_out, float* gm_out, const float* gp_bias, int B, int H, int W, int unit, cudaStream_t st);
 // k x k window sums of [B,1,H,W] (optionally of the squares)
 void launch_window_sum(const float* t, float* out, int B, int H, int W, int k, bool square, cudaStream_t st);
 

@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(256) update_kernel(const float* __restrict__ x
                                                      const float* __restrict__ lr, const float* __restrict__ structured,
                                                      const float* __restrict__ coeff_gl, float density, float lo, float hi,
                                                      int stage, float* __restrict__ gp_out, float* __restrict__ gm_out,
-                                                     int H, int W, int unit) {
+                                                     const float* __restrict__ gp_bias, int H, int W, int unit) {
   const int b = blockIdx.y, HW = H * W;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= HW) return;
@@ -519,7 +519,8 @@ __global__ void __launch_bounds__(256) update_kernel(const float* __restrict__ x
     float g = G[o];
     if (st != 0.f) g = fmaf(st, dLs[o], g);
     const float pv = pattern[o], xv = x[o];
-    const float gp = m * c * g;
+    float gp = m * c * g;
+    if (gp_bias != nullptr) gp = gp_bias[o] + gp;
     gm = fmaf((pv - xv) * c, g, gm);
     if (gp_out != nullptr) gp_out[o] = gp;
     if (step != 0.f) pattern[o] = fminf(fmaxf(pv - step * sgn(gp), lo), hi);
@@ -539,10 +540,10 @@ __global__ void __launch_bounds__(256) update_kernel(const float* __restrict__ x
 void launch_update(const float* x, float* mask, float* pattern, const float* G, const float* dLs,
                    const float* scale, const float* win_dev, const float* grp_ss, const float* lr,
                    const float* structured, const float* coeff_gl, float density, float lo, float hi, int stage,
-                   float* gp_out, float* gm_out, int B, int H, int W, int unit, cudaStream_t st) {
+                   float* gp_out, float* gm_out, const float* gp_bias, int B, int H, int W, int unit, cudaStream_t st) {
   update_kernel<<<dim3((H * W + 255) / 256, B), 256, 0, st>>>(x, mask, pattern, G, dLs, scale, win_dev, grp_ss, lr,
                                                               structured, coeff_gl, density, lo, hi, stage, gp_out,
-                                                              gm_out, H, W, unit);
+                                                              gm_out, gp_bias, H, W, unit);
 }
 
 // =====================================================================================

@@ -193,7 +193,7 @@ class Engine:
         return res
 
     def _update_args(self, x, mask, pattern, grad_adv, lr, structured, coeff_gl, density, stage, clip_min,
-                     clip_max, grad_pattern_out, grad_mask_out, host=False):
+                     clip_max, grad_pattern_out, grad_mask_out, host=False, grad_pattern_bias=None):
         B = x.shape[0]
         u = _lib.DpUpdateArgs()
         u.B, u.stage = B, int(stage)
@@ -207,16 +207,17 @@ class Engine:
             u.x, u.mask, u.pattern, u.grad_adv = _dev_ptr(x), _dev_ptr(mask), _dev_ptr(pattern), _dev_ptr(grad_adv)
             u.grad_pattern_out = _dev_ptr(grad_pattern_out)
             u.grad_mask_out = _dev_ptr(grad_mask_out)
+            u.grad_pattern_bias = _dev_ptr(grad_pattern_bias)
         u.lr_host, u.structured_host, u.coeff_gl_host = lrp, stp, cgp
         u.density, u.clip_min, u.clip_max = float(density), float(clip_min), float(clip_max)
         self._live_u = (lrh, sth, cgh)
         return u
 
     def attack_update(self, x, mask, pattern, grad_adv, lr, structured, coeff_gl, density, stage,
-                      clip_min=0.0, clip_max=1.0, grad_pattern_out=None, grad_mask_out=None):
+                      clip_min=0.0, clip_max=1.0, grad_pattern_out=None, grad_mask_out=None, grad_pattern_bias=None):
         """attack.py:332-342 (in place on mask / pattern)."""
         u = self._update_args(x, mask, pattern, grad_adv, lr, structured, coeff_gl, density, stage, clip_min,
-                              clip_max, grad_pattern_out, grad_mask_out)
+                              clip_max, grad_pattern_out, grad_mask_out, grad_pattern_bias=grad_pattern_bias)
         _lib.check(self.lib.dp_attack_update(self.handle, C.byref(u), self._stream()))
 
     def attack_step_host(self, x, mask, pattern, rects, y, crit_targeted, confidence, eps, stage, lr, structured,

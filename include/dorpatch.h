@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DP_ABI_VERSION 1
+#define DP_ABI_VERSION 2
 
 enum dp_precision {
   DP_PREC_FP32 = 0, /* fp32 storage, fp32 FMA math (no tensor cores): parity checks   */
@@ -152,6 +152,9 @@ typedef struct dp_update_args {
   float clip_min, clip_max;
   float* grad_pattern_out;     /* optional [B,3,H,W] dev: full d loss / d pattern     */
   float* grad_mask_out;        /* optional [B,1,H,W] dev: full d loss / d mask        */
+  const float* grad_pattern_bias; /* optional [B,3,H,W] dev, added to d loss / d pattern before the
+                                     sign: the stale stage-0 gradient the reference's first stage-1
+                                     step accumulates onto (attack.py:310-315 break precedes :342) */
 } dp_update_args;
 
 /* attack.py:332-342: theta -= lr * sign(grad theta); clip.  Must follow a

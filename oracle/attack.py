@@ -48,8 +48,9 @@ def cw_loss(logits, y, num_classes, targeted, confidence):
     onehot = torch.nn.functional.one_hot(y, num_classes)
     real = (logits * onehot).sum(1)
     other = ((1.0 - onehot) * logits - onehot * 1e4).max(1)[0]
-    margin = (other - real) if targeted else (real - other)
-    return torch.clamp(confidence + margin, min=0.0)
+    if targeted:                      # same association order as the reference: (conf + other) - real
+        return torch.clamp(confidence + other - real, min=0.0)
+    return torch.clamp(confidence + real - other, min=0.0)
 
 
 def local_variance(x):
@@ -284,6 +285,10 @@ def generate(model, x, patch_budget, n_classes, save_dir=None, batch_id=0, y=Non
     states = [ImageState(lr, structured, y[b], targeted, rngs[b]) for b in range(B)]
     dir_0 = os.path.dirname(save_dir.rstrip('/')) if save_dir else None
     last_logits = None
+    # Reference quirk (Q16): when stage 0 ends through the early-stop `break` (attack.py:310-315)
+    # the break precedes `adv_pattern.grad.zero_()` (:342), so the gradient of that last stage-0
+    # iteration is still in `.grad` and the first stage-1 backward accumulates onto it.
+    stale_grad_pattern = torch.zeros_like(adv_pattern)
 
     for stage in range(2):
         say('============= Stage %d =============' % stage)
@@ -344,6 +349,8 @@ def generate(model, x, patch_budget, n_classes, save_dir=None, batch_id=0, y=Non
                 model, x, adv_mask, adv_pattern, yv, idx, universe, [st.crit_targeted for st in states],
                 n_classes, confidence, [st.structured for st in states], density,
                 [st.coeff_group_lasso for st in states], stage, eps, local_var_x, idx2, basic_unit)
+            if stage == 1 and i == 0:
+                r["grad_pattern"] = stale_grad_pattern + r["grad_pattern"]
             last_logits = r["logits"].reshape(B, S, -1)
             loss_target = r["group_lasso"] if stage == 0 else r["loss_struc"]
             lr_used = np.zeros(B, dtype=np.float32)
@@ -363,6 +370,8 @@ def generate(model, x, patch_budget, n_classes, save_dir=None, batch_id=0, y=Non
                         mask_best[b] = adv_mask[b]
                         pattern_best[b] = adv_pattern[b]
                     st.active = False
+                    if stage == 0:
+                        stale_grad_pattern[b] = r["grad_pattern"][b]
                 else:
                     lr_used[b] = st.lr
                 stop_flags.append(stop)

@@ -1,0 +1,50 @@
+"""The N>1 path on CPU: world_size-2 gloo run of the step's only cross-rank exchange
+(all-reduce of the patch gradient + all-gather of the per-sample results) and of the
+EOT-shard slicing: the sharded result must equal the single-process result."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dorpatch_b200.attack import exchange_shards
+    B, S, HW = 3, 8, 5
+    rng = np.random.RandomState(0)
+    g_all = rng.rand(world, B, 3, HW, HW).astype(np.float32)          # per-rank partial gradient
+    loss = rng.rand(B, S).astype(np.float32)
+    preds = rng.randint(0, 1000, (B, S)).astype(np.int32)
+    s_loc = S // world
+    sl = slice(rank * s_loc, (rank + 1) * s_loc)
+    G = torch.from_numpy(g_all[rank].copy())
+    la, pa = exchange_shards(dist, G, loss[:, sl].copy(), preds[:, sl].copy())
+    ok = np.allclose(G.numpy(), g_all.sum(0), rtol=1e-6) and np.array_equal(la, loss) and np.array_equal(pa, preds)
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exchange_shards_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

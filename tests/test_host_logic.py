@@ -1,0 +1,143 @@
+"""CPU tests of the product's host-side logic (no GPU, no compute calls into the library):
+mask geometry, the scalar state machine, target selection, result paths, CLI surface, the C-ABI
+export list, and "no CPU fallback" behaviour."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import attack as OA
+from oracle import masks as OM
+from oracle import resnetv2 as OR
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_mask_tables_equal_oracle():
+    from dorpatch_b200 import masks as PM
+    for H in (56, 112, 224):
+        for d in (1, 2):
+            assert np.array_equal(PM.universe(H, d), OM.rects_to_array(OM.universe_rects(H, d)))
+    t = PM.universe(56, 2)
+    assert np.array_equal(PM.to_bool(t[:50], 56), OM.rects_to_bool(OM.universe_rects(56, 2)[:50], 56))
+    g = PM.gather(t, np.array([[0, 5]]), np.array([[7, 9]]))
+    assert g.shape == (1, 2, 4, 4) and np.array_equal(g[0, 1, 2:], t[9])
+
+
+def test_pick_target_equals_oracle_set_target():
+    from dorpatch_b200.attack import _pick_target
+    rng = np.random.RandomState(0)
+    for _ in range(300):
+        n = rng.randint(1, 9)
+        preds = rng.randint(0, 5, n)
+        label = int(rng.randint(0, 5))
+        assert _pick_target(preds, label) == OA.set_target(torch.from_numpy(preds), label)
+
+
+def test_bookkeeping_state_machine_equals_oracle():
+    """Random loss sequences through both state machines: identical lr / coefficients /
+    failed sets / decisions at every step (patience, lr decay, early stop included)."""
+    from dorpatch_b200.attack import _ImageState
+    for seed in range(4):
+        rng = np.random.RandomState(seed)
+        a = _ImageState(0.01, 1e-3, 3, False, np.random.RandomState(seed))
+        b = OA.ImageState(0.01, 1e-3, 3, False, np.random.RandomState(seed))
+        for stage in (0, 1):
+            a.reset()
+            b.reset_stage()
+            for i in range(1300):
+                ia, na = a.sample(i, 144, 8)
+                ib, nb = OA.sample_indices(b, i, 144, 8)
+                assert na == nb and np.array_equal(ia, ib)
+                loss = (rng.rand(8) < (0.3 if i < 900 else 0.9)).astype(np.float32) * 0.5 * (i < 1100 or rng.rand() < 0.5)
+                tgt = np.float32(10.0 / (1 + 0.01 * (i % 450)) + rng.rand() * 1e-3)
+                ra = a.bookkeeping(stage, i, loss, ia, na, tgt)
+                rb = OA.bookkeeping(b, stage, i, loss, ib, nb, tgt)
+                assert ra == rb
+                assert (a.lr, a.structured, a.coeff_group_lasso, a.failed, a.not_decay, a.num_failure) == \
+                       (b.lr, b.structured, b.coeff_group_lasso, b.failed, b.not_decay, b.num_failure)
+                if ra[1]:
+                    break
+
+
+def test_fp32_lr_decay_needs_two_decays():
+    """0.01f * 0.1f == float32(1e-3), which is NOT < 1e-3: the earliest stop is after the second decay."""
+    from dorpatch_b200.attack import _ImageState
+    s = _ImageState(0.01, 1e-3, 0, True, np.random.RandomState(0))
+    stops = []
+    for i in range(405):
+        _, stop = s.bookkeeping(1, i, np.zeros(2, np.float32), np.array([0, 1]), 0, 1.0)
+        stops.append(stop)
+    assert stops.index(True) == 402
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from dorpatch_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "dorpatch.h")).read()
+    declared = set(re.findall(r"\b(dp_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = _lib.load()
+    assert lib.dp_abi_version() == int(re.search(r"#define DP_ABI_VERSION (\d+)", header).group(1))
+    for name in declared:
+        assert hasattr(lib, name), "libdorpatch.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_no_cpu_fallback():
+    from dorpatch_b200.attack import DorPatch
+    from dorpatch_b200.resnetv2 import ResNetV2
+    from dorpatch_b200.utils import NormModel, get_normalize
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only behaviour")
+    net = ResNetV2()
+    model = torch.nn.DataParallel(NormModel(net, get_normalize("imagenet", "resnetv2")))
+    x = torch.rand(1, 3, 56, 56)
+    with pytest.raises(RuntimeError):
+        DorPatch().generate(model, x, 0.1, 1000, "results/a/b", 0)
+    with pytest.raises(RuntimeError):
+        net(x)
+    with pytest.raises(TypeError):          # an unsupported classifier is rejected, not silently run in eager mode
+        DorPatch().generate(torch.nn.Linear(3, 3), x, 0.1, 1000, "results/a/b", 0)
+    from dorpatch_b200.engine import Engine
+    with pytest.raises(RuntimeError):
+        Engine(img=56)
+
+
+def test_model_container_matches_oracle_params():
+    from dorpatch_b200.resnetv2 import ResNetV2
+    sd = ResNetV2(seed=0).state_dict()
+    ref = OR.random_init(seed=0)
+    assert list(sd.keys()) == list(ref.keys())
+    assert all(torch.equal(sd[k], ref[k]) for k in ref)
+
+
+def test_result_path_and_cli_surface(tmp_path, monkeypatch):
+    from dorpatch_b200 import main as M
+    from dorpatch_b200.utils import generate_saving_path
+    monkeypatch.chdir(tmp_path)
+    args = M.parser.parse_args(["--targeted", "--dropout", "1", "--synthetic", "3", "--max_iterations", "7"])
+    assert (args.batch_size, args.epsilon, args.lr, args.patch_budget, args.num_patch) == (1, 4.0, 0.01, 0.12, -1)
+    p = generate_saving_path(vars(args).copy())
+    assert p == ("results/dataset=imagenet_base_arch=resnetv2_targeted=True_attack=DorPatch_dropout=1_"
+                 "density=0.001_structured=0.001/num_patch=-1_patch_budget=0.12")
+    assert os.path.isdir(p)
+    ref_flags = ["--device", "--dataset", "--data_dir", "--model_dir", "--base_arch", "--targeted", "--patch_budget",
+                 "--attack", "--batch-size", "--epsilon", "--lr", "--num_patch", "--dropout", "--density", "--structured"]
+    have = {o for a in M.parser._actions for o in a.option_strings}
+    assert all(f in have for f in ref_flags)
+
+
+def test_reference_module_names_resolve():
+    import attack
+    import utils
+    from defenses.PatchCleanser import MaskWindow, PatchCleanser, PatchCleanserRecord, PatchCleanserResult  # noqa: F401
+    assert hasattr(attack, "DorPatch") and hasattr(attack.DorPatch, "generate")
+    for n in ("clip", "NormModel", "get_model", "get_dataset", "set_random_seed", "set_device", "generate_saving_path",
+              "NUM_CLASSES_DICT", "convert_float_list_to_str"):
+        assert hasattr(utils, n), n
+    import pickle
+    rec = PatchCleanserRecord(3, True, np.arange(36), np.ones(630, bool))
+    back = pickle.loads(pickle.dumps([[rec]]))
+    assert back[0][0].prediction == 3 and back[0][0].preds_2.shape == (630,)
