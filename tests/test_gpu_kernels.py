@@ -81,11 +81,31 @@ def test_expand_matches_occlude_normalise(engine_factory, precision, H, S):
         assert torch.equal(got[..., :3], ref.bfloat16().float())
 
 
-@pytest.mark.parametrize("precision,tol_logit,min_cos", [("fp32", 2e-3, 0.999), ("tf32", 3e-2, 0.99), ("bf16", 8e-2, 0.97)])
+def _torch_gpu_reference(params, z, dl, precision):
+    """The same network in PyTorch on the GPU at the given arithmetic: what the reference itself
+    would compute on a GPU (its default is TF32 convolutions, utils.py:17 / torch defaults)."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = precision != "fp32"
+    try:
+        pg = {k: v.to(DEV) for k, v in params.items()}
+        zc = z.to(DEV).requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(precision == "bf16")):
+            out = OR.forward_normalized(pg, zc)
+        (out.float() * dl.to(DEV)).sum().backward()
+        return out.float().detach().cpu(), zc.grad.cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("precision,tol_logit,min_cos", [("fp32", 2e-3, 0.999), ("tf32", None, None), ("bf16", None, None)])
 def test_classifier_forward_backward(engine_factory, oracle_params, precision, tol_logit, min_cos):
     """ResNetV2-50 logits and d/d(input) vs torch-CPU autograd on the oracle restatement.
     fp32: |dlogit| <= 2e-3, grad cosine >= 0.999 (ReLU / max-pool ties flip on last-bit
-    differences, so gradients are compared by cosine, not element-wise)."""
+    differences, so gradients are compared by cosine, not element-wise).
+    tf32 / bf16: the random-init network is chaotic in its input gradient (PyTorch's own GPU
+    run at the same arithmetic drifts from fp32-CPU by the same amount -- measured cos 0.94 /
+    0.52), so the bar is "no further from the fp32 oracle than PyTorch-GPU at that arithmetic":
+    logit error <= 2x PyTorch's + 5e-3, gradient cosine >= PyTorch's - 0.05."""
     H, N = 112, 3
     e = engine_factory(img=H, precision=precision, chunk=8, max_images=4)
     z = (_rand((N, 3, H, H), 11) - 0.5) * 2
@@ -100,6 +120,12 @@ def test_classifier_forward_backward(engine_factory, oracle_params, precision, t
     err = (logits.cpu() - ref.detach()).abs().max().item()
     cos = _cos(dz.cpu(), zr.grad)
     print("precision", precision, "logit err", err, "grad cos", cos, "rel", _rel(dz.cpu(), zr.grad))
+    if precision != "fp32":
+        t_logits, t_grad = _torch_gpu_reference(oracle_params, z, dl, precision)
+        t_err = (t_logits - ref.detach()).abs().max().item()
+        t_cos = _cos(t_grad, zr.grad)
+        print("  torch-GPU at", precision, ": logit err", t_err, "grad cos", t_cos)
+        tol_logit, min_cos = 2 * t_err + 5e-3, t_cos - 0.05
     assert err <= tol_logit, err
     assert cos >= min_cos, cos
 
