@@ -83,7 +83,7 @@ def cpu_step_factory(S):
     # "all the host threads it can use": torch-CPU convolutions on a 16-sample batch get SLOWER when
     # oversubscribed (128 threads: 0.14 samples/s on the GPU box), so pick the fastest thread count.
     cores = os.cpu_count() or 1
-    cand = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+    cand = sorted({c for c in (8, 16, 32, 64, cores) if c <= min(cores, 64)})
     zt = torch.rand(4, 3, IMG, IMG).requires_grad_(True)
     best_t, best_dt = cand[0], float("inf")
     for c in cand:
@@ -262,6 +262,13 @@ def run_native(args):
     W, K = max(args.warmup, 3), args.steps
     for i in range(W):
         step(i)
+    if args.ncu:       # one step between cudaProfilerStart/Stop for `ncu --profile-from-start off`
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(W)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
@@ -373,6 +380,7 @@ def main():
     ap.add_argument("--eot", type=int, default=S_PER_GPU)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="run W warm-up steps, then ONE step inside cudaProfilerStart/Stop, and exit")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
