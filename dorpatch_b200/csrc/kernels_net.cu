@@ -6,8 +6,15 @@
 // resnetv2_50x1_bit_distilled, /root/reference/utils.py:51-58): StdConv2d eps=1e-8,
 // GroupNormAct(32 groups, eps=1e-5, ReLU), stem 'fixed' (ConstantPad2d(1,0)+MaxPool 3x3/2).
 // These kernels are HBM-bound; every one is a coalesced 16-byte-vector pass.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace dp {
 
@@ -243,8 +250,8 @@ void launch_gn_stats(const void* x, float* partial, float* stats, int N, int P, 
   DISPATCH_T(bf16, (gn_finalize_kernel<T><<<N, 32, 0, st>>>(partial, stats, P, C, splits)));
 }
 
-void launch_gn_relu_forward(const void* x, void* y, const float* gamma, const float* beta, float* partial,
-                            float* stats, int N, int P, int C, bool bf16, cudaStream_t st) {
+void launch_gn_relu_forward_2pass(const void* x, void* y, const float* gamma, const float* beta, float* partial,
+                                  float* stats, int N, int P, int C, bool bf16, cudaStream_t st) {
   const int splits = gn_splits(P, C, bf16);
   DISPATCH_T(bf16, (gn_stats_kernel<T><<<dim3(splits, N), GN_THREADS, 0, st>>>((const T*)x, partial, P, C, splits)));
   DISPATCH_T(bf16, (gn_apply_kernel<T><<<dim3(apply_slabs(P, C, Vec<T>::N), N), GN_THREADS, 0, st>>>(
@@ -344,14 +351,288 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(const T* __res
   }
 }
 
-void launch_gn_relu_backward(const void* dy, const void* x, const void* addend, void* dx, const float* gamma,
-                             const float* beta, const float* stats, float* partial, int N, int P, int C, bool bf16,
-                             cudaStream_t st) {
+void launch_gn_relu_backward_2pass(const void* dy, const void* x, const void* addend, void* dx, const float* gamma,
+                                   const float* beta, const float* stats, float* partial, int N, int P, int C, bool bf16,
+                                   cudaStream_t st) {
   const int splits = gn_splits(P, C, bf16);
   DISPATCH_T(bf16, (gn_bwd_reduce_kernel<T><<<dim3(splits, N), GN_THREADS, 0, st>>>(
                        (const T*)dy, (const T*)x, gamma, beta, stats, partial, P, C, splits)));
   DISPATCH_T(bf16, (gn_bwd_apply_kernel<T><<<dim3(apply_slabs(P, C, Vec<T>::N), N), GN_THREADS, 0, st>>>(
                        (const T*)dy, (const T*)x, (const T*)addend, (T*)dx, gamma, beta, stats, partial, P, C, splits)));
+}
+
+// ------------------------------------------------------------------------------------
+// Cluster-per-sample GroupNorm: ONE HBM read of the input.  A thread-block cluster of CL
+// CTAs owns one sample; each CTA pulls its contiguous pixel slab into shared memory with TMA
+// bulk copies (cp.async.bulk + mbarrier), reduces it to per-group partial sums, the cluster
+// combines the partials through distributed shared memory in rank order (deterministic), and
+// every CTA normalises its slab straight out of shared memory.
+//   forward : HBM traffic = read x + write y            (two-pass version: 2 reads + 1 write)
+//   backward: x slab stays in shared memory; dy is streamed twice (second pass hits L2, the
+//             slab was read microseconds earlier by the same SM): read x, dy (+addend), write dx.
+// ------------------------------------------------------------------------------------
+namespace gnc {
+constexpr int THREADS = 256;
+constexpr int MAX_GPT = 4;                       // groups per thread (V / cpg when cpg < V)
+constexpr size_t HDR = 1024;                     // mbarrier + cluster partials + stats
+constexpr size_t TP_BYTES = (size_t)THREADS * MAX_GPT * 2 * sizeof(float);
+constexpr uint32_t BULK_CHUNK = 32768;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void slab_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    for (uint32_t off = 0; off < bytes; off += BULK_CHUNK) {
+      const uint32_t nb = bytes - off < BULK_CHUNK ? bytes - off : BULK_CHUNK;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32((const char*)dst + off)),
+                   "l"((const char*)src + off), "r"(nb), "r"(smem_u32(bar))
+                   : "memory");
+    }
+  }
+}
+__device__ __forceinline__ void slab_wait(uint64_t* bar) {
+  __syncthreads();   // the init by thread 0 is visible before anyone polls
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(0u)
+        : "memory");
+  }
+}
+
+// Deterministic CTA reduction of per-thread per-channel accumulators (a[V], b[V]) to per-group
+// sums; thread t owns vector column (t % cols), rows t / cols.  Result in part[g*2 + {0,1}].
+template <int V>
+__device__ __forceinline__ void cta_group_reduce(const float* a, const float* b, int C, float* tp, float* part) {
+  const int cols = C / V, cpg = C / GN_GROUPS;
+  const int gpt = cpg >= V ? 1 : V / cpg;                 // groups per thread
+  const int cpv = cpg >= V ? V : cpg;                     // channels per (thread, group)
+  for (int j = 0; j < gpt; ++j) {
+    float sa = 0.f, sb = 0.f;
+    for (int i = 0; i < cpv; ++i) { sa += a[j * cpv + i]; sb += b[j * cpv + i]; }
+    tp[(threadIdx.x * MAX_GPT + j) * 2 + 0] = sa;
+    tp[(threadIdx.x * MAX_GPT + j) * 2 + 1] = sb;
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS) {
+    const int g = threadIdx.x, rpi = THREADS / cols;
+    int c_lo, c_hi, j;
+    if (cpg >= V) { c_lo = g * (cpg / V); c_hi = c_lo + cpg / V; j = 0; }
+    else { c_lo = g / gpt; c_hi = c_lo + 1; j = g % gpt; }
+    float sa = 0.f, sb = 0.f;
+    for (int r = 0; r < rpi; ++r)
+      for (int c = c_lo; c < c_hi; ++c) {
+        const int t = r * cols + c;
+        sa += tp[(t * MAX_GPT + j) * 2 + 0];
+        sb += tp[(t * MAX_GPT + j) * 2 + 1];
+      }
+    part[g * 2 + 0] = sa;
+    part[g * 2 + 1] = sb;
+  }
+}
+}  // namespace gnc
+
+template <typename T>
+__global__ void __launch_bounds__(gnc::THREADS) gn_fwd_cluster_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                                       const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta,
+                                                                       float* __restrict__ stats, int P, int C) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ __align__(128) unsigned char smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int n = blockIdx.x / CL;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  float* part = reinterpret_cast<float*>(smem + 64);          // [32][2] this CTA's partials
+  float* s_mean = reinterpret_cast<float*>(smem + 64 + 256);  // [32]
+  float* s_rstd = s_mean + GN_GROUPS;                         // [32]
+  float* tp = reinterpret_cast<float*>(smem + gnc::HDR);
+  T* slab = reinterpret_cast<T*>(smem + gnc::HDR + gnc::TP_BYTES);
+
+  const int p0 = (int)(((long long)P * rank) / CL), p1 = (int)(((long long)P * (rank + 1)) / CL);
+  const int rows = p1 - p0;
+  const T* src = x + ((size_t)n * P + p0) * C;
+  gnc::slab_load(slab, src, (uint32_t)((size_t)rows * C * sizeof(T)), bar);
+  gnc::slab_wait(bar);
+
+  const int cols = C / V, rpi = gnc::THREADS / cols, cpg = C / GN_GROUPS;
+  const int tcol = threadIdx.x % cols, trow = threadIdx.x / cols;
+  float a[V], b[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { a[i] = 0.f; b[i] = 0.f; }
+  for (int r = trow; r < rows; r += rpi) {
+    Vec<T> v; v.load(slab + (size_t)r * C + tcol * V);
+    float f[V]; v.unpack(f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { a[i] += f[i]; b[i] = fmaf(f[i], f[i], b[i]); }
+  }
+  gnc::cta_group_reduce<V>(a, b, C, tp, part);
+  cluster.sync();
+  if (threadIdx.x < GN_GROUPS) {
+    float s = 0.f, q = 0.f;
+    for (int r = 0; r < CL; ++r) {
+      const float* rp = cluster.map_shared_rank(part, r);
+      s += rp[threadIdx.x * 2 + 0];
+      q += rp[threadIdx.x * 2 + 1];
+    }
+    const float cnt = (float)P * cpg;
+    const float mean = s / cnt;
+    float var = q / cnt - mean * mean;
+    var = var < 0.f ? 0.f : var;
+    const float rstd = rsqrtf(var + 1e-5f);
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rstd;
+    if (rank == 0) {
+      stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 0] = mean;
+      stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 1] = rstd;
+    }
+  }
+  __syncthreads();
+  float sa[V], sb[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = tcol * V + i, g = c / cpg;
+    sa[i] = s_rstd[g] * gamma[c];
+    sb[i] = beta[c] - s_mean[g] * sa[i];
+  }
+  T* dst = y + ((size_t)n * P + p0) * C;
+  for (int r = trow; r < rows; r += rpi) {
+    Vec<T> v; v.load(slab + (size_t)r * C + tcol * V);
+    float f[V]; v.unpack(f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) f[i] = fmaxf(fmaf(sa[i], f[i], sb[i]), 0.f);
+    v.pack(f); v.store(dst + (size_t)r * C + tcol * V);
+  }
+  cluster.sync();   // nobody leaves while a peer may still read its partials
+}
+
+template <typename T>
+__global__ void __launch_bounds__(gnc::THREADS) gn_bwd_cluster_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                       const T* __restrict__ addend, T* __restrict__ dx,
+                                                                       const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta,
+                                                                       const float* __restrict__ stats, int P, int C) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ __align__(128) unsigned char smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int n = blockIdx.x / CL;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  float* part = reinterpret_cast<float*>(smem + 64);
+  float* s_1 = reinterpret_cast<float*>(smem + 64 + 256);
+  float* s_2 = s_1 + GN_GROUPS;
+  float* tp = reinterpret_cast<float*>(smem + gnc::HDR);
+  T* slab = reinterpret_cast<T*>(smem + gnc::HDR + gnc::TP_BYTES);
+
+  const int p0 = (int)(((long long)P * rank) / CL), p1 = (int)(((long long)P * (rank + 1)) / CL);
+  const int rows = p1 - p0;
+  const size_t base = ((size_t)n * P + p0) * C;
+  gnc::slab_load(slab, x + base, (uint32_t)((size_t)rows * C * sizeof(T)), bar);
+
+  const int cols = C / V, rpi = gnc::THREADS / cols, cpg = C / GN_GROUPS;
+  const int tcol = threadIdx.x % cols, trow = threadIdx.x / cols;
+  float ga[V], sa[V], sb[V], mu[V], rs[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = tcol * V + i, g = c / cpg;
+    ga[i] = gamma[c];
+    mu[i] = stats[((size_t)n * GN_GROUPS + g) * 2 + 0];
+    rs[i] = stats[((size_t)n * GN_GROUPS + g) * 2 + 1];
+    sa[i] = rs[i] * ga[i];
+    sb[i] = beta[c] - mu[i] * sa[i];
+  }
+  gnc::slab_wait(bar);
+  float a[V], b[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { a[i] = 0.f; b[i] = 0.f; }
+  for (int r = trow; r < rows; r += rpi) {
+    Vec<T> vx, vd; vx.load(slab + (size_t)r * C + tcol * V); vd.load(dy + base + (size_t)r * C + tcol * V);
+    float fx[V], fd[V]; vx.unpack(fx); vd.unpack(fd);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float pre = fmaf(sa[i], fx[i], sb[i]);
+      const float dg = pre > 0.f ? fd[i] * ga[i] : 0.f;
+      const float xh = (fx[i] - mu[i]) * rs[i];
+      a[i] += dg; b[i] = fmaf(dg, xh, b[i]);
+    }
+  }
+  gnc::cta_group_reduce<V>(a, b, C, tp, part);
+  cluster.sync();
+  if (threadIdx.x < GN_GROUPS) {
+    float s = 0.f, q = 0.f;
+    for (int r = 0; r < CL; ++r) {
+      const float* rp = cluster.map_shared_rank(part, r);
+      s += rp[threadIdx.x * 2 + 0];
+      q += rp[threadIdx.x * 2 + 1];
+    }
+    const float inv_m = 1.0f / ((float)P * cpg);
+    s_1[threadIdx.x] = s * inv_m;
+    s_2[threadIdx.x] = q * inv_m;
+  }
+  __syncthreads();
+  float m1[V], m2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { const int g = (tcol * V + i) / cpg; m1[i] = s_1[g]; m2[i] = s_2[g]; }
+  for (int r = trow; r < rows; r += rpi) {
+    const size_t off = base + (size_t)r * C + tcol * V;
+    Vec<T> vx, vd; vx.load(slab + (size_t)r * C + tcol * V); vd.load(dy + off);
+    float fx[V], fd[V], fo[V]; vx.unpack(fx); vd.unpack(fd);
+    if (addend != nullptr) { Vec<T> va; va.load(addend + off); va.unpack(fo); }
+    else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) fo[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float pre = fmaf(sa[i], fx[i], sb[i]);
+      const float dg = pre > 0.f ? fd[i] * ga[i] : 0.f;
+      const float xh = (fx[i] - mu[i]) * rs[i];
+      fo[i] += rs[i] * (dg - m1[i] - xh * m2[i]);
+    }
+    Vec<T> vo; vo.pack(fo); vo.store(dx + off);
+  }
+  cluster.sync();
+}
+
+// cluster size for a [P, C] sample of element size es: smallest power of two whose slab fits the
+// per-CTA budget (two CTAs per SM when possible); 0 = does not fit -> two-pass fallback.
+static int gn_cluster_size(int P, int C, size_t es, size_t* smem_out) {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("DORPATCH_GN"); mode = (e && strcmp(e, "twopass") == 0) ? 0 : 1; }
+  if (!mode) return 0;
+  if (C / (int)(16 / es) > gnc::THREADS) return 0;
+  const size_t total = (size_t)P * C * es, fixed = gnc::HDR + gnc::TP_BYTES;
+  const size_t soft = 100 * 1024, hard = 220 * 1024;
+  for (int cl = 1; cl <= 8; cl *= 2) {
+    if (cl > P) break;
+    const size_t slab = ((size_t)((P + cl - 1) / cl)) * C * es;
+    if (slab + fixed <= soft || (cl == 8 && slab + fixed <= hard)) { *smem_out = slab + fixed; return cl; }
+  }
+  (void)total;
+  return 0;
+}
+
+template <typename K, typename... Args>
+static bool launch_cluster(K kernel, int cl, int nblocks, size_t smem, cudaStream_t st, Args... args) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nblocks);
+  cfg.blockDim = dim3(gnc::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...) == cudaSuccess;
 }
 
 // ------------------------------------------------------------------------------------
@@ -585,6 +866,35 @@ void launch_subsample2_adjoint_add(const void* dy, void* dx, int N, int H, int W
     size_t total = (size_t)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / Vec<T>::N);
     subsample2_adj_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const T*)dy, (T*)dx, H, W, C, total);
   });
+}
+
+void launch_gn_relu_forward(const void* x, void* y, const float* gamma, const float* beta, float* partial,
+                            float* stats, int N, int P, int C, bool bf16, cudaStream_t st) {
+  size_t smem = 0;
+  const int cl = gn_cluster_size(P, C, bf16 ? 2 : 4, &smem);
+  if (cl > 0) {
+    bool ok;
+    if (bf16) ok = launch_cluster(gn_fwd_cluster_kernel<__nv_bfloat16>, cl, cl * N, smem, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, stats, P, C);
+    else ok = launch_cluster(gn_fwd_cluster_kernel<float>, cl, cl * N, smem, st, (const float*)x, (float*)y, gamma, beta, stats, P, C);
+    if (ok) return;
+    cudaGetLastError();   // clear and fall back
+  }
+  launch_gn_relu_forward_2pass(x, y, gamma, beta, partial, stats, N, P, C, bf16, st);
+}
+
+void launch_gn_relu_backward(const void* dy, const void* x, const void* addend, void* dx, const float* gamma,
+                             const float* beta, const float* stats, float* partial, int N, int P, int C, bool bf16,
+                             cudaStream_t st) {
+  size_t smem = 0;
+  const int cl = gn_cluster_size(P, C, bf16 ? 2 : 4, &smem);
+  if (cl > 0) {
+    bool ok;
+    if (bf16) ok = launch_cluster(gn_bwd_cluster_kernel<__nv_bfloat16>, cl, cl * N, smem, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)addend, (__nv_bfloat16*)dx, gamma, beta, stats, P, C);
+    else ok = launch_cluster(gn_bwd_cluster_kernel<float>, cl, cl * N, smem, st, (const float*)dy, (const float*)x, (const float*)addend, (float*)dx, gamma, beta, stats, P, C);
+    if (ok) return;
+    cudaGetLastError();
+  }
+  launch_gn_relu_backward_2pass(dy, x, addend, dx, gamma, beta, stats, partial, N, P, C, bf16, st);
 }
 
 }  // namespace dp

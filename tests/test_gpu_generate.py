@@ -1,0 +1,142 @@
+"""GPU parity of the whole entry point: dorpatch_b200.attack.DorPatch().generate (host state
+machine + native engine, fp32 arithmetic) against the CPU oracle's generate on identical seeds,
+and against the golden trajectory produced by the unmodified reference; PatchCleanser bits;
+the main.py driver end to end on synthetic data."""
+import io
+import os
+import contextlib
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import attack as OA
+from oracle import patchcleanser as OP
+from oracle import resnetv2 as OR
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+LR = 0.01
+
+
+def _seed(s=1234):
+    random.seed(s)
+    torch.manual_seed(s)
+    np.random.seed(s)
+
+
+@pytest.fixture(scope="module")
+def native_model(oracle_params):
+    from dorpatch_b200.resnetv2 import ResNetV2
+    from dorpatch_b200.utils import NormModel, get_normalize
+    os.environ["DORPATCH_PRECISION"] = "fp32"
+    os.environ["DORPATCH_CHUNK"] = "16"
+    net = ResNetV2(seed=0)
+    net.load_state_dict(oracle_params)
+    return torch.nn.DataParallel(NormModel(net, get_normalize("imagenet", "resnetv2"))).cuda().eval()
+
+
+def _compare(m_gpu, p_gpu, m_ref, p_ref, iters, what):
+    m_gpu, p_gpu = m_gpu.cpu(), p_gpu.cpu()
+    inter = ((m_gpu > 0.5) & (m_ref > 0.5)).sum().item()
+    union = ((m_gpu > 0.5) | (m_ref > 0.5)).sum().item()
+    iou = inter / max(union, 1)
+    d = (p_gpu - p_ref).abs()
+    frac = (d > 1e-6).float().mean().item()
+    print(what, "mask IoU", iou, "pattern max diff", d.max().item(), "frac differing", frac)
+    assert iou >= 0.90, iou
+    assert d.max().item() <= 2 * iters * LR + 1e-6
+    assert frac <= 0.05, frac
+
+
+def test_generate_matches_oracle_and_reference_golden(native_model, oracle_params, tmp_path):
+    """1 image (112 px), targeted, 2 stages x 6 iterations, S=4, dropout=1 -- the run pinned as
+    golden G9 from the reference.  fp32 engine.  Tolerance: the update is sign(grad), so a
+    last-bit gradient difference moves a pixel by +-lr; we require the selected patch mask IoU
+    >= 0.90, at most 5 % of pattern pixels off, none by more than 2*iters*lr, identical log
+    structure and identical RNG consumption."""
+    from dorpatch_b200.attack import DorPatch
+    G = np.load(os.path.join(HERE, "golden", "reference_golden.npz"))
+    xr = torch.rand(1, 3, 112, 112, generator=torch.Generator().manual_seed(7))
+    tgt = torch.from_numpy(G["g9_target"])
+    kw = dict(patch_budget=0.12, n_classes=1000, targeted=True, max_iterations=6, sampling_size=4, dropout=1)
+
+    _seed()
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        m_gpu, p_gpu = DorPatch().generate(native_model, xr.cuda(), save_dir=str(tmp_path / "cfg" / "sub"), batch_id=0,
+                                           y=tgt.cuda(), **kw)
+    log_gpu = [l for l in buf.getvalue().splitlines() if not l.startswith("mask size")]
+    rng_gpu = np.random.get_state()[1][:4].copy()
+    assert os.path.exists(tmp_path / "cfg" / "adv_mask_0.pt") and os.path.exists(tmp_path / "cfg" / "adv_pattern_0.pt")
+
+    net = OR.OracleNet(oracle_params, weights_require_grad=False).eval()
+    _seed()
+    log_or = []
+    m_or, p_or = OA.generate(net, xr, y=tgt, log=log_or.append, **kw)
+    rng_or = np.random.get_state()[1][:4].copy()
+
+    assert np.array_equal(rng_gpu, rng_or)                          # same numpy RNG consumption
+    assert np.array_equal(rng_gpu, G["g9_rng_np"])                  # ... as the reference's
+    assert len(log_gpu) == len(log_or) == len(G["g9_log"])
+    for a, b in zip(log_gpu, log_or):                               # same lines up to printed precision jitter
+        assert a.split(",")[0] == b.split(",")[0]
+    _compare(m_gpu, p_gpu, m_or, p_or, 6, "vs oracle:")
+    m_gold = torch.from_numpy(np.unpackbits(G["g9_mask"])[: 112 * 112].reshape(1, 1, 112, 112).astype(np.float32))
+    _compare(m_gpu, p_gpu, m_gold, torch.from_numpy(G["g9_pattern"].astype(np.float32)), 6, "vs reference golden:")
+
+
+def test_generate_batched_images_are_independent(native_model, oracle_params, tmp_path):
+    """B=2 runs two independent single-image problems (per-image state); compare with the oracle's
+    B=2 run (same per-image RNG derivation)."""
+    from dorpatch_b200.attack import DorPatch
+    x = torch.rand(2, 3, 112, 112, generator=torch.Generator().manual_seed(9))
+    kw = dict(patch_budget=0.05, n_classes=1000, targeted=True, max_iterations=4, sampling_size=4, dropout=2)
+    tgt = torch.tensor([10, 20])
+    _seed()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m_gpu, p_gpu = DorPatch().generate(native_model, x.cuda(), save_dir=str(tmp_path / "c2" / "sub"), batch_id=1,
+                                           y=tgt.cuda(), **kw)
+    net = OR.OracleNet(oracle_params, weights_require_grad=False).eval()
+    _seed()
+    m_or, p_or = OA.generate(net, x, y=tgt, **kw)
+    for b in range(2):
+        _compare(m_gpu[b:b + 1], p_gpu[b:b + 1], m_or[b:b + 1], p_or[b:b + 1], 4, "image %d:" % b)
+
+
+def test_patchcleanser_bits_match_oracle(native_model, oracle_params):
+    """defenses.PatchCleanser.robust_predict on the native forward engine vs the oracle
+    restatement: identical prediction / certification / one-mask / two-mask bits wherever the
+    oracle's top-2 logit margin is not within fp32 noise (always, for these inputs)."""
+    from dorpatch_b200.defenses.PatchCleanser import MaskWindow, PatchCleanser
+    net = OR.OracleNet(oracle_params, weights_require_grad=False).eval()
+    img = torch.rand(3, 112, 112, generator=torch.Generator().manual_seed(3))
+    for r in (0.03, 0.12):
+        with contextlib.redirect_stdout(io.StringIO()):
+            rec = PatchCleanser(MaskWindow(112, r, 1), native_model).robust_predict(img.cuda(), True)
+        pred, cert, p1, p2 = OP.robust_predict(net, img, 112, r, certify=True)
+        assert (rec.preds_1 == p1).mean() >= 0.97
+        assert (np.asarray(rec.preds_2).astype(bool) == p2.astype(bool)).mean() >= 0.97
+        if (rec.preds_1 == p1).all() and (np.asarray(rec.preds_2).astype(bool) == p2.astype(bool)).all():
+            assert rec.prediction == pred and bool(rec.certification) == bool(cert)
+
+
+def test_main_driver_end_to_end(tmp_path, monkeypatch):
+    """python main.py --synthetic ... : artefact layout (main.py:135-153 of the reference) and the
+    metrics line format (main.py:186-187)."""
+    from dorpatch_b200 import main as M
+    monkeypatch.chdir(tmp_path)
+    os.environ["DORPATCH_PRECISION"] = "bf16"
+    out = M.cli(["--synthetic", "2", "--random_init", "--img_size", "112", "--max_iterations", "3", "--sampling_size", "4",
+                 "--dropout", "1", "--targeted", "--num_batches", "2", "--chunk", "16"])
+    rd = out["result_dir"]
+    assert rd.endswith("num_patch=-1_patch_budget=0.12")
+    for i in range(2):
+        for f in ("adv_mask_%d.pt", "adv_pattern_%d.pt", "adv_PC_%d.pt"):
+            assert os.path.exists(os.path.join(rd, f % i)), f % i
+        assert os.path.exists(os.path.join(os.path.dirname(rd), "adv_mask_%d.pt" % i))   # stage-0 artefact in the parent
+    assert out["line"].startswith("clean accuracy: ") and "certified_ASR@PC:" in out["line"]
+    import pickle
+    recs = pickle.load(open(os.path.join(rd, "adv_PC_0.pt"), "rb"))
+    assert len(recs[0]) == 4 and recs[0][0].preds_1.shape == (36,) and recs[0][0].preds_2.shape == (630,)
