@@ -91,6 +91,8 @@ struct GemmPlan {
   cublasLtMatmulDesc_t op = nullptr;
   cublasLtMatrixLayout_t a = nullptr, b = nullptr, c = nullptr;
   cublasLtMatmulAlgo_t algo;
+  std::vector<cublasLtMatmulAlgo_t> candidates;   // heuristic top-k, timed on first use when autotune is on
+  bool tuned = false;
 };
 
 }  // namespace
@@ -463,17 +465,41 @@ struct dp_engine {
     cublasLtMatmulPreference_t pref;
     CUBLAS_OK(cublasLtMatmulPreferenceCreate(&pref));
     CUBLAS_OK(cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES, &lib_ws_bytes, sizeof(lib_ws_bytes)));
-    cublasLtMatmulHeuristicResult_t res[4];
+    cublasLtMatmulHeuristicResult_t res[8];
     int got = 0;
-    cublasStatus_t s = cublasLtMatmulAlgoGetHeuristic(lt, p.op, p.a, p.b, p.c, p.c, pref, 4, res, &got);
+    cublasStatus_t s = cublasLtMatmulAlgoGetHeuristic(lt, p.op, p.a, p.b, p.c, p.c, pref, 8, res, &got);
     cublasLtMatmulPreferenceDestroy(pref);
     if (s != CUBLAS_STATUS_SUCCESS || got == 0) fail("cublasLt: no algorithm for GEMM rows=%d nout=%d k=%d mode=%d (status %d)", rows, nout, k, mode, (int)s);
     p.algo = res[0].algo;
+    for (int i = 0; i < got; ++i)
+      if (res[i].state == CUBLAS_STATUS_SUCCESS) p.candidates.push_back(res[i].algo);
     return gemm_plans.emplace(key, p).first->second;
   }
   void gemm(int rows, int nout, int k, int mode, const void* W, const void* X, const void* Cres, float beta, void* D, cudaStream_t st) {
     GemmPlan& p = gemm_plan(rows, nout, k, mode);
     const float one = 1.f;
+    // Autotune (once per shape): time the heuristic's top candidates on the real operands.  Skipped
+    // for in-place accumulation (C == D), where repeated trial runs would corrupt the addend.
+    const bool in_place_acc = (beta != 0.f) && (Cres == nullptr || Cres == D);
+    if (!p.tuned && cfg.autotune && !in_place_acc && p.candidates.size() > 1 && !prof_on) {
+      cudaEvent_t e0, e1;
+      CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+      float best = 1e30f;
+      for (auto& cand : p.candidates) {
+        bool ok = true;
+        for (int rep = 0; rep < 3 && ok; ++rep) {
+          if (rep == 1) CUDA_OK(cudaEventRecord(e0, st));
+          ok = cublasLtMatmul(lt, p.op, &one, W, p.a, X, p.b, &beta, Cres ? Cres : D, p.c, D, p.c, &cand, lib_ws, lib_ws_bytes, st) == CUBLAS_STATUS_SUCCESS;
+        }
+        if (!ok) continue;
+        CUDA_OK(cudaEventRecord(e1, st));
+        CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0.f; CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) { best = ms; p.algo = cand; }
+      }
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+      p.tuned = true;
+    }
     const double by = ((double)rows * k + (double)rows * nout * (beta != 0.f ? 2 : 1) + (double)nout * k) * es;
     PROF(this, mode == 0 ? "gemm1x1_fwd" : "gemm1x1_bwd", by, 2.0 * rows * nout * k, st,
          CUBLAS_OK(cublasLtMatmul(lt, p.op, &one, W, p.a, X, p.b, &beta, Cres ? Cres : D, p.c, D, p.c, &p.algo, lib_ws, lib_ws_bytes, st)));
