@@ -409,15 +409,18 @@ struct dp_engine {
       CUDNN_OK(cudnnFindConvolutionBackwardDataAlgorithmEx(cudnn, c.wdesc, c.w, p.ydesc, dy, c.cdesc, p.xdesc, dx, 16, &got, perf, lib_ws, lib_ws_bytes));
     else
       CUDNN_OK(cudnnGetConvolutionBackwardDataAlgorithm_v7(cudnn, c.wdesc, p.ydesc, c.cdesc, p.xdesc, 16, &got, perf));
-    int fallback = -1;
+    // results are sorted by time: take the fastest usable one, but prefer a deterministic algorithm
+    // when it is within 25 % of it (a slow "deterministic" dgrad once cost 688 ms on the stem).
+    int fastest = -1, det = -1;
     for (int i = 0; i < got; ++i) {
       if (perf[i].status != CUDNN_STATUS_SUCCESS || perf[i].memory > lib_ws_bytes || !math_ok(perf[i].mathType)) continue;
-      if (perf[i].determinism != CUDNN_DETERMINISTIC) { if (fallback < 0) fallback = i; continue; }
-      p.bwd_algo = perf[i].algo; p.bwd_math = perf[i].mathType; p.bwd_ws = perf[i].memory; p.bwd_ready = true;
-      return;
+      if (fastest < 0) fastest = i;
+      if (det < 0 && perf[i].determinism == CUDNN_DETERMINISTIC) det = i;
     }
-    if (fallback >= 0) {
-      p.bwd_algo = perf[fallback].algo; p.bwd_math = perf[fallback].mathType; p.bwd_ws = perf[fallback].memory; p.bwd_ready = true;
+    if (fastest >= 0) {
+      int pick = fastest;
+      if (det >= 0 && (!cfg.autotune || perf[det].time <= 1.25f * perf[fastest].time)) pick = det;
+      p.bwd_algo = perf[pick].algo; p.bwd_math = perf[pick].mathType; p.bwd_ws = perf[pick].memory; p.bwd_ready = true;
       return;
     }
     fail("no usable cuDNN backward-data algorithm (cin=%d cout=%d k=%d stride=%d, %d candidates)", c.cin_pad, c.cout, c.k, c.stride, got);

@@ -553,15 +553,28 @@ __global__ void __launch_bounds__(gnc::THREADS) gn_bwd_cluster_kernel(const T* _
   float a[V], b[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) { a[i] = 0.f; b[i] = 0.f; }
-  for (int r = trow; r < rows; r += rpi) {
-    Vec<T> vx, vd; vx.load(slab + (size_t)r * C + tcol * V); vd.load(dy + base + (size_t)r * C + tcol * V);
-    float fx[V], fd[V]; vx.unpack(fx); vd.unpack(fd);
+  constexpr int U = 4;   // independent global loads in flight per thread
+  for (int r0 = trow; r0 < rows; r0 += rpi * U) {
+    Vec<T> vd[U];
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float pre = fmaf(sa[i], fx[i], sb[i]);
-      const float dg = pre > 0.f ? fd[i] * ga[i] : 0.f;
-      const float xh = (fx[i] - mu[i]) * rs[i];
-      a[i] += dg; b[i] = fmaf(dg, xh, b[i]);
+    for (int u = 0; u < U; ++u) {
+      const int r = r0 + u * rpi;
+      if (r < rows) vd[u].load(dy + base + (size_t)r * C + tcol * V);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = r0 + u * rpi;
+      if (r < rows) {
+        Vec<T> vx; vx.load(slab + (size_t)r * C + tcol * V);
+        float fx[V], fd[V]; vx.unpack(fx); vd[u].unpack(fd);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float pre = fmaf(sa[i], fx[i], sb[i]);
+          const float dg = pre > 0.f ? fd[i] * ga[i] : 0.f;
+          const float xh = (fx[i] - mu[i]) * rs[i];
+          a[i] += dg; b[i] = fmaf(dg, xh, b[i]);
+        }
+      }
     }
   }
   gnc::cta_group_reduce<V>(a, b, C, tp, part);
@@ -581,23 +594,39 @@ __global__ void __launch_bounds__(gnc::THREADS) gn_bwd_cluster_kernel(const T* _
   float m1[V], m2[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) { const int g = (tcol * V + i) / cpg; m1[i] = s_1[g]; m2[i] = s_2[g]; }
-  for (int r = trow; r < rows; r += rpi) {
-    const size_t off = base + (size_t)r * C + tcol * V;
-    Vec<T> vx, vd; vx.load(slab + (size_t)r * C + tcol * V); vd.load(dy + off);
-    float fx[V], fd[V], fo[V]; vx.unpack(fx); vd.unpack(fd);
-    if (addend != nullptr) { Vec<T> va; va.load(addend + off); va.unpack(fo); }
-    else {
+  for (int r0 = trow; r0 < rows; r0 += rpi * U) {
+    Vec<T> vd[U], va[U];
 #pragma unroll
-      for (int i = 0; i < V; ++i) fo[i] = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int r = r0 + u * rpi;
+      if (r < rows) {
+        const size_t off = base + (size_t)r * C + tcol * V;
+        vd[u].load(dy + off);
+        if (addend != nullptr) va[u].load(addend + off);
+      }
     }
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float pre = fmaf(sa[i], fx[i], sb[i]);
-      const float dg = pre > 0.f ? fd[i] * ga[i] : 0.f;
-      const float xh = (fx[i] - mu[i]) * rs[i];
-      fo[i] += rs[i] * (dg - m1[i] - xh * m2[i]);
+    for (int u = 0; u < U; ++u) {
+      const int r = r0 + u * rpi;
+      if (r < rows) {
+        const size_t off = base + (size_t)r * C + tcol * V;
+        Vec<T> vx; vx.load(slab + (size_t)r * C + tcol * V);
+        float fx[V], fd[V], fo[V]; vx.unpack(fx); vd[u].unpack(fd);
+        if (addend != nullptr) va[u].unpack(fo);
+        else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) fo[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float pre = fmaf(sa[i], fx[i], sb[i]);
+          const float dg = pre > 0.f ? fd[i] * ga[i] : 0.f;
+          const float xh = (fx[i] - mu[i]) * rs[i];
+          fo[i] += rs[i] * (dg - m1[i] - xh * m2[i]);
+        }
+        Vec<T> vo; vo.pack(fo); vo.store(dx + off);
+      }
     }
-    Vec<T> vo; vo.pack(fo); vo.store(dx + off);
   }
   cluster.sync();
 }
