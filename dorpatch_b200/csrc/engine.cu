@@ -63,6 +63,7 @@ thread_local std::string g_last_error;
 constexpr int DEPTHS[4] = {3, 4, 6, 3};
 constexpr int WIDTHS[4] = {256, 512, 1024, 2048};
 constexpr int STEM_CH = 64;
+constexpr int STEM_SUB = 128;   // samples per cuDNN stem-conv call
 constexpr int UNIT = 7;   // basic_unit of the group lasso / patch selection (attack.py:52)
 
 struct ConvW {            // one convolution's weights (device, KRSC, activation dtype)
@@ -101,7 +102,10 @@ struct dp_engine {
   dp_config cfg;
   bool bf16 = false;
   size_t es = 4;            // activation element size
-  int Cp = 4;               // padded input channels
+  int Cp = 4;               // channels per pixel of the network INPUT (3 = tight, own stem kernel)
+  int Cpd = 4;              // channels per pixel of d(input) produced by the library dgrad (4 fp32 / 8 bf16)
+  bool own_stem = false;    // bf16: hand-written tensor-core stem forward on the tight C=3 layout
+  void* stem_w_kn = nullptr;
   int H = 224, K = 1000, chunk = 64;
   int num_sms = 148;
   cudnnHandle_t cudnn = nullptr;
@@ -222,7 +226,7 @@ struct dp_engine {
       m = std::max(m, (size_t)b.hin * b.hin * std::max(b.cin, b.mid));
       m = std::max(m, (size_t)b.hout * b.hout * b.cout);
     }
-    m = std::max(m, (size_t)H * H * Cp);
+    m = std::max(m, (size_t)H * H * std::max(Cp, Cpd));
     return m;
   }
 
@@ -265,7 +269,8 @@ struct dp_engine {
 
   void allocate() {
     const size_t n = (size_t)chunk;
-    make_conv(stem, 3, STEM_CH, 7, 2, 3, Cp);
+    make_conv(stem, 3, STEM_CH, 7, 2, 3, Cpd);
+    if (own_stem) stem_w_kn = dmalloc((size_t)160 * 64 * 2);
     for (auto& b : blocks) {
       make_gn(b.n1, b.cin); make_gn(b.n2, b.mid); make_gn(b.n3, b.mid);
       if (b.has_ds) make_conv(b.ds, b.cin, b.cout, 1, b.stride, 0, b.cin);
@@ -339,6 +344,7 @@ struct dp_engine {
     try {
       int i = get("stem.conv.weight");
       upload_conv(stem, ptrs[i], numels[i], st, tmp);
+      if (own_stem) { dp::launch_stem_pack(stem.w, stem_w_kn, stem.cin_pad, st); KERNEL_OK(); CUDA_OK(cudaStreamSynchronize(st)); }
       int s = 0, bi = 0;
       for (auto& b : blocks) {
         char pre[64];
@@ -516,7 +522,16 @@ struct dp_engine {
     if (N > chunk) fail("forward: N=%d exceeds chunk=%d", N, chunk);
     CUDNN_OK(cudnnSetStream(cudnn, st));
     const int hs = Hs(), hp = Hp();
-    conv_fwd(0, stem, N, H, hs, input, act, st);
+    if (own_stem) {
+      PROF(this, "stem_conv_fwd", ((double)N * H * H * 3 + (double)N * hs * hs * STEM_CH) * es, 2.0 * N * hs * hs * STEM_CH * 147, st,
+           dp::launch_stem_forward(input, stem_w_kn, act, N, H, H, st));
+      KERNEL_OK(); ++launches;
+    } else {
+      for (int n0 = 0; n0 < N; n0 += STEM_SUB) {   // cuDNN's stem kernels degrade badly beyond ~128 samples of 224x224
+        const int n = std::min(STEM_SUB, N - n0);
+        conv_fwd(0, stem, n, H, hs, (const char*)input + (size_t)n0 * H * H * Cp * es, (char*)act + (size_t)n0 * hs * hs * STEM_CH * es, st);
+      }
+    }
     PROF(this, "maxpool_fwd", (double)N * (hs * hs + hp * hp) * STEM_CH * es, 0, st,
          dp::launch_maxpool_forward(act, x0, train ? pool_amax : nullptr, N, hs, hs, STEM_CH, bf16, st)); KERNEL_OK(); ++launches;
     const void* cur = x0;
@@ -598,7 +613,10 @@ struct dp_engine {
     const int hs = Hs();
     PROF(this, "maxpool_bwd", (double)N * (hs * hs + (hs / 2) * (hs / 2)) * STEM_CH * es, 0, st,
          dp::launch_maxpool_backward(GA, pool_amax, GB, N, hs, hs, STEM_CH, bf16, st)); KERNEL_OK(); ++launches;
-    conv_bwd(0, stem, N, H, hs, GB, GC, st);
+    for (int n0 = 0; n0 < N; n0 += STEM_SUB) {
+      const int n = std::min(STEM_SUB, N - n0);
+      conv_bwd(0, stem, n, H, hs, (const char*)GB + (size_t)n0 * hs * hs * STEM_CH * es, (char*)GC + (size_t)n0 * H * H * Cpd * es, st);
+    }
     d_input = GC;
   }
 
@@ -659,9 +677,12 @@ int32_t dp_engine_create(const dp_config* cfg, dp_engine** out) {
     e->num_sms = prop.multiProcessorCount;
     e->bf16 = (cfg->precision == DP_PREC_BF16);
     e->es = e->bf16 ? 2 : 4;
-    e->Cp = e->bf16 ? 8 : 4;
-    if (const char* s = getenv("DORPATCH_CPAD")) e->Cp = atoi(s);
-    if (e->Cp != 3 && e->Cp != 4 && e->Cp != 8) fail("DORPATCH_CPAD must be 3, 4 or 8");
+    e->Cpd = e->bf16 ? 8 : 4;
+    if (const char* s = getenv("DORPATCH_CPAD")) e->Cpd = atoi(s);
+    if (e->Cpd != 4 && e->Cpd != 8) fail("DORPATCH_CPAD must be 4 or 8");
+    const char* stem_env = getenv("DORPATCH_STEM");
+    e->own_stem = e->bf16 && !(stem_env && strcmp(stem_env, "cudnn") == 0);
+    e->Cp = e->own_stem ? 3 : e->Cpd;
     e->H = cfg->img; e->K = cfg->n_classes; e->chunk = cfg->chunk;
     e->cudnn_dt = e->bf16 ? CUDNN_DATA_BFLOAT16 : CUDNN_DATA_FLOAT;
     e->cuda_dt = e->bf16 ? CUDA_R_16BF : CUDA_R_32F;
@@ -866,7 +887,7 @@ static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t
     KERNEL_OK(); ++e->launches;
     e->backward(n, e->dlogits, st);
     PROF(e, "reduce_k1t", (double)n * H * H * 3 * e->es + 3.0 * H * H * 4 * (double)n / S, 0, st,
-         dp::launch_reduce(e->d_input, rects, a->grad_adv, B, S, n0, n, H, H, e->Cp, e->bf16, st)); KERNEL_OK(); ++e->launches;
+         dp::launch_reduce(e->d_input, rects, a->grad_adv, B, S, n0, n, H, H, e->Cpd, e->bf16, st)); KERNEL_OK(); ++e->launches;
   }
   // results -> host (pinned staging, one sync)
   unsigned char* out = e->pin + d2h_off;
@@ -959,7 +980,7 @@ int32_t dp_net_forward_backward(dp_engine* e, const float* z, int32_t N, float* 
   if (dlogits_dev) {
     if (!dz_dev) fail("dz_dev is required when dlogits_dev is given");
     e->backward(N, dlogits_dev, st);
-    dp::launch_unpack_nhwc(e->d_input, dz_dev, N, e->H, e->H, e->Cp, e->bf16, st); KERNEL_OK(); ++e->launches;
+    dp::launch_unpack_nhwc(e->d_input, dz_dev, N, e->H, e->H, e->Cpd, e->bf16, st); KERNEL_OK(); ++e->launches;
   }
   DP_CATCH
 }

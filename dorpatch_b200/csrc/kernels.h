@@ -44,6 +44,10 @@ void launch_pool_grad_bcast(const float* dpooled, void* dy, int N, int P, int C,
 void launch_subsample2(const void* x, void* y, int N, int H, int W, int C, bool bf16, cudaStream_t st);
 void launch_subsample2_adjoint_add(const void* dy, void* dx, int N, int H, int W, int C, bool bf16, cudaStream_t st);
 
+// ---- hand-written bf16 tensor-core stem convolution on the tight C=3 input (kernels_stem.cu)
+void launch_stem_pack(const void* w_krsc, void* w_kn, int cin_pad, cudaStream_t st);
+void launch_stem_forward(const void* in, const void* w_kn, void* out, int N, int H, int W, cudaStream_t st);
+
 // ---- patch-side kernels (kernels_patch.cu) -------------------------------------------
 // utils.clip + add: adv_x = x + min(eps/||m(p-x)||,1) * m(p-x); l2[b], scale[b] dev outputs.
 void launch_paste(const float* x, const float* mask, const float* pattern, float* adv_x, float* l2, float* scale,

@@ -1,0 +1,132 @@
+// kernels_stem.cu -- hand-written tensor-core stem convolution (bf16): 7x7 stride 2 pad 3, 3 -> 64.
+//
+// The classifier's first layer (timm ResNetV2 'fixed' stem, StdConv2d 7x7/2; reference call site
+// /root/reference/utils.py:78 -> timm) has only 3 input channels: library kernels want the channel
+// dimension padded to 8 (bf16), which (i) makes K1 write 8/3 of the algorithmic bytes and (ii) runs
+// at ~23 TFLOP/s in cuDNN.  This kernel reads the TIGHT NHWC C=3 layout K1 produces, builds the
+// im2col tile in shared memory and runs mma.sync.m16n8k16 (bf16 in, fp32 accumulate).
+//   CTA = 256 threads = 8 warps; tile = 8 x 16 output pixels x 64 channels; K = 147 -> 160.
+//   A CTA walks all x-tiles of one (sample, tile-row): the 20 KB weight matrix is loaded once.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace dp {
+namespace stem {
+constexpr int TOY = 8, TOX = 16, TM = TOY * TOX;       // output tile
+constexpr int KR = 147, KP = 160;                      // real / padded reduction length
+constexpr int PR = 2 * TOY + 5, PC = 2 * TOX + 5;      // input patch 21 x 37 pixels
+constexpr int PSTRIDE = PC * 3 + 1;                    // 112 elements per patch row
+constexpr int ASTRIDE = KP + 8;                        // 168: conflict-free ldmatrix rows (336 B)
+constexpr int BSTRIDE = 64 + 8;                        // 72: conflict-free (144 B)
+constexpr int THREADS = 256;
+constexpr size_t SMEM = (size_t)(PR * PSTRIDE + TM * ASTRIDE + KP * BSTRIDE) * 2;
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
+__device__ __forceinline__ void mma_bf16(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+}  // namespace stem
+
+// w_kn: [KP][64] bf16, row k = (ky*7+kx)*3 + c (rows >= 147 are zero).  in: [N,H,W,3] bf16.  out: [N,H/2,W/2,64].
+__global__ void __launch_bounds__(stem::THREADS) stem_fwd_kernel(const __nv_bfloat16* __restrict__ in,
+                                                                  const __nv_bfloat16* __restrict__ w_kn,
+                                                                  __nv_bfloat16* __restrict__ out, int H, int W) {
+  using namespace stem;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* As = patch + PR * PSTRIDE;
+  __nv_bfloat16* Bs = As + TM * ASTRIDE;
+  const int Ho = H / 2, Wo = W / 2;
+  const int n = blockIdx.y, oy0 = blockIdx.x * TOY;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < KP * 64; i += THREADS) Bs[(i >> 6) * BSTRIDE + (i & 63)] = w_kn[i];
+  for (int i = threadIdx.x; i < TM * (KP - KR); i += THREADS)                        // zero the K padding once
+    As[(i / (KP - KR)) * ASTRIDE + KR + i % (KP - KR)] = __float2bfloat16(0.f);
+
+  const __nv_bfloat16* in_n = in + (size_t)n * H * W * 3;
+  const int ntx = (Wo + TOX - 1) / TOX;
+  for (int tx = 0; tx < ntx; ++tx) {
+    const int ox0 = tx * TOX;
+    const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
+    __syncthreads();                                                                // previous tile's MMAs done
+    for (int i = threadIdx.x; i < PR * PC * 3; i += THREADS) {
+      const int r = i / (PC * 3), e = i % (PC * 3);
+      const int iy = iy0 + r, ix = ix0 + e / 3;
+      __nv_bfloat16 v = __float2bfloat16(0.f);
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = in_n[((size_t)iy * W + ix0) * 3 + e];
+      patch[r * PSTRIDE + e] = v;
+    }
+    __syncthreads();
+    // im2col: A[m][ky*21 + j] = patch[2*py + ky][6*px + j], j < 21
+    for (int i = threadIdx.x; i < TM * 7; i += THREADS) {
+      const int m = i / 7, ky = i % 7, py = m / TOX, px = m % TOX;
+      const __nv_bfloat16* src = patch + (2 * py + ky) * PSTRIDE + 6 * px;
+      __nv_bfloat16* dst = As + m * ASTRIDE + ky * 21;
+#pragma unroll
+      for (int j = 0; j < 21; ++j) dst[j] = src[j];
+    }
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+    const int m0 = warp * 16;
+#pragma unroll
+    for (int ks = 0; ks < KP / 16; ++ks) {
+      uint32_t a0, a1, a2, a3;
+      ldmatrix_x4(a0, a1, a2, a3, As + (m0 + (lane & 15)) * ASTRIDE + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {                                              // two n8 tiles per ldmatrix
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4_trans(b0, b1, b2, b3, Bs + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * BSTRIDE + np * 16 + (lane >> 4) * 8);
+        mma_bf16(acc[2 * np], a0, a1, a2, a3, b0, b1);
+        mma_bf16(acc[2 * np + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+    const int g = lane >> 2, t4 = lane & 3;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int m = m0 + g + half * 8, oy = oy0 + m / TOX, ox = ox0 + m % TOX;
+      if (oy < Ho && ox < Wo) {
+        __nv_bfloat16* o = out + (((size_t)n * Ho + oy) * Wo + ox) * 64;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          *reinterpret_cast<__nv_bfloat162*>(o + nt * 8 + 2 * t4) = __floats2bfloat162_rn(acc[nt][half * 2], acc[nt][half * 2 + 1]);
+      }
+    }
+  }
+}
+
+// KRSC (cin padded to cin_pad) -> [160][64] K-major matrix for the kernel above
+__global__ void stem_pack_kernel(const __nv_bfloat16* __restrict__ w_krsc, __nv_bfloat16* __restrict__ w_kn, int cin_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= stem::KP * 64) return;
+  const int k = i >> 6, n = i & 63;
+  __nv_bfloat16 v = __float2bfloat16(0.f);
+  if (k < stem::KR) { const int tap = k / 3, c = k % 3; v = w_krsc[((size_t)n * 49 + tap) * cin_pad + c]; }
+  w_kn[i] = v;
+}
+
+void launch_stem_pack(const void* w_krsc, void* w_kn, int cin_pad, cudaStream_t st) {
+  stem_pack_kernel<<<(stem::KP * 64 + 255) / 256, 256, 0, st>>>((const __nv_bfloat16*)w_krsc, (__nv_bfloat16*)w_kn, cin_pad);
+}
+void launch_stem_forward(const void* in, const void* w_kn, void* out, int N, int H, int W, cudaStream_t st) {
+  cudaFuncSetAttribute(stem_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem::SMEM);
+  const int Ho = H / 2;
+  dim3 grid((Ho + stem::TOY - 1) / stem::TOY, N);
+  stem_fwd_kernel<<<grid, stem::THREADS, stem::SMEM, st>>>((const __nv_bfloat16*)in, (const __nv_bfloat16*)w_kn, (__nv_bfloat16*)out, H, W);
+}
+
+}  // namespace dp

@@ -43,8 +43,11 @@ def _compare(m_gpu, p_gpu, m_ref, p_ref, iters, what):
     union = ((m_gpu > 0.5) | (m_ref > 0.5)).sum().item()
     iou = inter / max(union, 1)
     d = (p_gpu - p_ref).abs()
-    frac = (d > 1e-6).float().mean().item()
-    print(what, "mask IoU", iou, "pattern max diff", d.max().item(), "frac differing", frac)
+    # a flipped sign moves a stage-1 pixel by a whole lr; everything smaller is the (global) L2-clip
+    # scale / stage-0 flips seen through the ~0.1x clip scale
+    frac = (d > 0.25 * LR).float().mean().item()
+    print(what, "mask IoU", iou, "pattern max diff", d.max().item(), "mean diff", d.mean().item(),
+          "frac off by > lr/4", frac)
     assert iou >= 0.90, iou
     assert d.max().item() <= 2 * iters * LR + 1e-6
     assert frac <= 0.05, frac
@@ -81,6 +84,8 @@ def test_generate_matches_oracle_and_reference_golden(native_model, oracle_param
     assert np.array_equal(rng_gpu, G["g9_rng_np"])                  # ... as the reference's
     assert len(log_gpu) == len(log_or) == len(G["g9_log"])
     for a, b in zip(log_gpu, log_or):                               # same lines up to printed precision jitter
+        print("GPU:", a)
+        print("ORA:", b)
         assert a.split(",")[0] == b.split(",")[0]
     _compare(m_gpu, p_gpu, m_or, p_or, 6, "vs oracle:")
     m_gold = torch.from_numpy(np.unpackbits(G["g9_mask"])[: 112 * 112].reshape(1, 1, 112, 112).astype(np.float32))
