@@ -103,6 +103,8 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 
 constexpr int EXP_R = 4;          // image rows per tile
 constexpr int EXP_THREADS = 256;
+constexpr int EXP_G = 4;          // samples staged per barrier phase
+constexpr int EXP_SETS = 2;       // double-buffered staging sets
 
 __device__ __forceinline__ bool rect_hit(const short* r, int row, int col) {
 #pragma unroll
@@ -123,19 +125,26 @@ struct ExpandParams {
   int B, S, n0, n, H, W, sgroups;
 };
 
+// Shared-memory layout (dynamic): [mbarrier 128 B][rects EXP_G*16 shorts, 128 B][input planes NP*R*W fp32]
+// [clean tile][EXP_SETS*EXP_G staging tiles].  A tile is R full image rows in the output layout
+// (W*CP elements of T per row), i.e. ONE contiguous run of the output tensor -> one bulk store.
 template <typename T, int CP, bool FUSED>
 __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
   constexpr int NP = FUSED ? 7 : 3;
+  constexpr int EPC = 16 / (int)sizeof(T);                 // elements per 16-byte chunk
   extern __shared__ __align__(128) unsigned char smem[];
   const int W = p.W, H = p.H, HW = H * W;
   const int tile_px = EXP_R * W;
   const uint32_t plane_bytes = (uint32_t)tile_px * 4u;
   const uint32_t out_bytes = (uint32_t)tile_px * CP * (uint32_t)sizeof(T);
+  const int row_chunks = W * CP / EPC, tile_chunks = EXP_R * row_chunks;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-  float* in = reinterpret_cast<float*>(smem + 128);
-  T* clean = reinterpret_cast<T*>(smem + 128 + NP * plane_bytes);
-  T* stage0 = reinterpret_cast<T*>(smem + 128 + NP * plane_bytes + out_bytes);
-  T* stage1 = reinterpret_cast<T*>(smem + 128 + NP * plane_bytes + 2 * out_bytes);
+  short* srect_all = reinterpret_cast<short*>(smem + 128);                        // [EXP_SETS][EXP_G][16]
+  int* stouch_all = reinterpret_cast<int*>(smem + 128 + EXP_SETS * EXP_G * 32);  // [EXP_SETS][EXP_G]
+  float* in = reinterpret_cast<float*>(smem + 512);
+  unsigned char* clean_b = smem + 512 + NP * plane_bytes;
+  T* clean = reinterpret_cast<T*>(clean_b);
+  unsigned char* stage_b = clean_b + out_bytes;
 
   if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); ptx::fence_proxy_async(); }
   __syncthreads();
@@ -144,20 +153,19 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
   const int tiles = H / EXP_R;
   const int items = (b_last - b_first + 1) * tiles * p.sgroups;
   uint32_t phase = 0;
-  int stage_sel = 0;
+  int set = 0;
 
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int sg = item % p.sgroups;
     const int tile = (item / p.sgroups) % tiles;
     const int b = b_first + item / (p.sgroups * tiles);
-    // samples of image b inside [n0, n0+n), split into sgroups
     const int lo = max(p.n0, b * p.S), hi = min(p.n0 + p.n, (b + 1) * p.S);
     const int cnt = hi - lo;
     const int s_lo = lo + (int)(((long long)cnt * sg) / p.sgroups), s_hi = lo + (int)(((long long)cnt * (sg + 1)) / p.sgroups);
     if (s_lo >= s_hi) continue;   // uniform across the CTA
     const int r0 = tile * EXP_R;
 
-    // previous item's bulk stores must have finished READING clean/stage before we overwrite
+    // every bulk store of the previous item must have finished READING the clean tile
     if (threadIdx.x == 0) ptx::bulk_wait_read<0>();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -191,44 +199,64 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
     ptx::fence_proxy_async();
     __syncthreads();
 
-    for (int n = s_lo; n < s_hi; ++n) {
-      T* dst = reinterpret_cast<T*>(p.out) + ((size_t)(n - p.n0) * HW + (size_t)r0 * W) * CP;
-      short r[16];
-      bool touch = false;
-      if (p.rects != nullptr) {
-        const int4* rp = reinterpret_cast<const int4*>(p.rects + (size_t)n * 16);
-        int4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
-        *reinterpret_cast<int4*>(r) = q0;
-        *reinterpret_cast<int4*>(r + 8) = q1;
-        touch = rect_rows_hit(r, r0, r0 + EXP_R);
+    for (int nb = s_lo; nb < s_hi; nb += EXP_G) {
+      const int g_cnt = min(EXP_G, s_hi - nb);
+      short* srect = srect_all + set * EXP_G * 16;     // per-set copies: thread 0 may still be issuing the
+      int* stouch = stouch_all + set * EXP_G;          // previous batch's stores while others run ahead
+      // ---- which samples of this batch have an occluder crossing the tile rows?
+      if (threadIdx.x < g_cnt) {
+        const int g = threadIdx.x;
+        int touch = 0;
+        if (p.rects != nullptr) {
+          const int4* rp = reinterpret_cast<const int4*>(p.rects + (size_t)(nb + g) * 16);
+          const int4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
+          *reinterpret_cast<int4*>(srect + g * 16) = q0;
+          *reinterpret_cast<int4*>(srect + g * 16 + 8) = q1;
+          touch = rect_rows_hit(srect + g * 16, r0, r0 + EXP_R) ? 1 : 0;
+        }
+        stouch[g] = touch;
       }
-      if (!touch) {
-        if (threadIdx.x == 0) { ptx::bulk_store(dst, clean, out_bytes); ptx::bulk_commit(); }
-        continue;
-      }
-      T* stg = stage_sel ? stage1 : stage0;
-      stage_sel ^= 1;
-      // the bulk store that last used this staging tile must have finished reading it
-      if (threadIdx.x == 0) ptx::bulk_wait_read<1>();
+      // the staging set we are about to overwrite was last used two batches ago
+      if (threadIdx.x == 0) ptx::bulk_wait_read<EXP_SETS - 1>();
       __syncthreads();
-      if (CP * sizeof(T) == 16) {
-        const uint4* cs = reinterpret_cast<const uint4*>(clean);
-        uint4* ds = reinterpret_cast<uint4*>(stg);
-        for (int i = threadIdx.x; i < tile_px; i += EXP_THREADS) {
-          const int row = r0 + i / W, col = i % W;
-          ds[i] = rect_hit(r, row, col) ? make_uint4(0u, 0u, 0u, 0u) : cs[i];
-        }
-      } else {
-        for (int i = threadIdx.x; i < tile_px; i += EXP_THREADS) {
-          const int row = r0 + i / W, col = i % W;
-          const bool z = rect_hit(r, row, col);
+      unsigned char* set_b = stage_b + (size_t)set * EXP_G * out_bytes;
+      // ---- compose the occluded tiles: 16-byte chunks, interval tests per chunk
+      for (int idx = threadIdx.x; idx < g_cnt * tile_chunks; idx += EXP_THREADS) {
+        const int g = idx / tile_chunks, ch = idx % tile_chunks;
+        if (!stouch[g]) continue;
+        const int row = r0 + ch / row_chunks, e0 = (ch % row_chunks) * EPC;
+        const short* r = srect + g * 16;
+        bool zero = false, partial = false;
 #pragma unroll
-          for (int c = 0; c < CP; ++c) stg[i * CP + c] = z ? from_float<T>(0.f) : clean[i * CP + c];
+        for (int k = 0; k < 4; ++k) {
+          if (row >= r[4 * k] && row < r[4 * k + 1]) {
+            const int lo_e = r[4 * k + 2] * CP, hi_e = r[4 * k + 3] * CP;
+            if (hi_e > lo_e) {
+              if (e0 >= lo_e && e0 + EPC <= hi_e) zero = true;
+              else if (e0 < hi_e && e0 + EPC > lo_e) partial = true;
+            }
+          }
         }
+        uint4 v = reinterpret_cast<const uint4*>(clean_b)[ch];
+        if (zero) v = make_uint4(0u, 0u, 0u, 0u);
+        else if (partial) {
+          T* ev = reinterpret_cast<T*>(&v);
+#pragma unroll
+          for (int k = 0; k < EPC; ++k)
+            if (rect_hit(r, row, (e0 + k) / CP)) ev[k] = from_float<T>(0.f);
+        }
+        reinterpret_cast<uint4*>(set_b + (size_t)g * out_bytes)[ch] = v;
       }
       ptx::fence_proxy_async();
       __syncthreads();
-      if (threadIdx.x == 0) { ptx::bulk_store(dst, stg, out_bytes); ptx::bulk_commit(); }
+      if (threadIdx.x == 0) {
+        for (int g = 0; g < g_cnt; ++g) {
+          T* dst = reinterpret_cast<T*>(p.out) + ((size_t)(nb + g - p.n0) * HW + (size_t)r0 * W) * CP;
+          ptx::bulk_store(dst, stouch[g] ? (const void*)(set_b + (size_t)g * out_bytes) : (const void*)clean_b, out_bytes);
+        }
+        ptx::bulk_commit();
+      }
+      set ^= 1;
     }
   }
   if (threadIdx.x == 0) ptx::bulk_wait_read<0>();
@@ -237,15 +265,18 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
 
 template <typename T, int CP, bool FUSED>
 static void expand_launch(const ExpandParams& p, int num_sms, cudaStream_t st) {
-  const size_t smem = 128 + (size_t)(FUSED ? 7 : 3) * EXP_R * p.W * 4 + 3 * (size_t)EXP_R * p.W * CP * sizeof(T);
+  const size_t out_bytes = (size_t)EXP_R * p.W * CP * sizeof(T);
+  const size_t smem = 512 + (size_t)(FUSED ? 7 : 3) * EXP_R * p.W * 4 + (1 + EXP_SETS * EXP_G) * out_bytes;
   cudaFuncSetAttribute(expand_kernel<T, CP, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ExpandParams q = p;
   const int nb = (p.n0 + p.n - 1) / p.S - p.n0 / p.S + 1;
   const int tiles = p.H / EXP_R;
-  const int ctas_per_sm = 3;
+  int ctas_per_sm = (int)((220 * 1024) / smem);
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 4) ctas_per_sm = 4;
   const int target = num_sms * ctas_per_sm;
   int sg = 1;
-  while (nb * tiles * sg < target && sg < p.S && sg < 32) sg *= 2;
+  while (nb * tiles * sg < target && sg * EXP_G < p.S && sg < 32) sg *= 2;
   q.sgroups = sg;
   int grid = nb * tiles * sg;
   if (grid > target) grid = target;
