@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    try:
+        import torch
+        torch.set_num_threads(max(1, min(32, os.cpu_count() or 1)))
+    except Exception:
+        pass
 
 
 @pytest.fixture(scope="session")
@@ -22,7 +27,8 @@ def oracle_params():
 def oracle_net(oracle_params):
     import torch
     from oracle import resnetv2 as R
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    # torch-CPU convolutions get much slower when oversubscribed (128 threads on the GPU box)
+    torch.set_num_threads(max(1, min(32, os.cpu_count() or 1)))
     return R.OracleNet(oracle_params, weights_require_grad=False).eval()
 
 
