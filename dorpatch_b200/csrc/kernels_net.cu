@@ -415,11 +415,18 @@ __device__ __forceinline__ void cta_group_reduce(const float* a, const float* b,
   const int cols = C / V, cpg = C / GN_GROUPS;
   const int gpt = cpg >= V ? 1 : V / cpg;                 // groups per thread
   const int cpv = cpg >= V ? V : cpg;                     // channels per (thread, group)
-  for (int j = 0; j < gpt; ++j) {
+  // static indices only: a[] / b[] must stay in registers (dynamic indexing would spill the hot
+  // loop's accumulators to local memory)
+#pragma unroll
+  for (int j = 0; j < MAX_GPT; ++j) {
     float sa = 0.f, sb = 0.f;
-    for (int i = 0; i < cpv; ++i) { sa += a[j * cpv + i]; sb += b[j * cpv + i]; }
-    tp[(threadIdx.x * MAX_GPT + j) * 2 + 0] = sa;
-    tp[(threadIdx.x * MAX_GPT + j) * 2 + 1] = sb;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      if (i / cpv == j) { sa += a[i]; sb += b[i]; }
+    if (j < gpt) {
+      tp[(threadIdx.x * MAX_GPT + j) * 2 + 0] = sa;
+      tp[(threadIdx.x * MAX_GPT + j) * 2 + 1] = sb;
+    }
   }
   __syncthreads();
   if (threadIdx.x < GN_GROUPS) {
