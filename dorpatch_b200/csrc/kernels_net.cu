@@ -503,6 +503,7 @@ __global__ void __launch_bounds__(gnc::THREADS) gn_fwd_cluster_kernel(const T* _
     }
   }
   __syncthreads();
+  cluster.barrier_arrive();   // our remote reads are done; peers may exit once everyone has arrived
   float sa[V], sb[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(gnc::THREADS) gn_fwd_cluster_kernel(const T* _
     for (int i = 0; i < V; ++i) f[i] = fmaxf(fmaf(sa[i], f[i], sb[i]), 0.f);
     v.pack(f); v.store(dst + (size_t)r * C + tcol * V);
   }
-  cluster.sync();   // nobody leaves while a peer may still read its partials
+  cluster.barrier_wait();   // nobody leaves while a peer may still read its partials
 }
 
 template <typename T>
@@ -598,6 +599,7 @@ __global__ void __launch_bounds__(gnc::THREADS) gn_bwd_cluster_kernel(const T* _
     s_2[threadIdx.x] = q * inv_m;
   }
   __syncthreads();
+  cluster.barrier_arrive();
   float m1[V], m2[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) { const int g = (tcol * V + i) / cpg; m1[i] = s_1[g]; m2[i] = s_2[g]; }
@@ -635,7 +637,7 @@ __global__ void __launch_bounds__(gnc::THREADS) gn_bwd_cluster_kernel(const T* _
       }
     }
   }
-  cluster.sync();
+  cluster.barrier_wait();
 }
 
 // cluster size for a [P, C] sample of element size es: smallest power of two whose slab fits the
@@ -646,7 +648,7 @@ static int gn_cluster_size(int P, int C, size_t es, size_t* smem_out) {
   if (!mode) return 0;
   if (C / (int)(16 / es) > gnc::THREADS) return 0;
   const size_t total = (size_t)P * C * es, fixed = gnc::HDR + gnc::TP_BYTES;
-  const size_t soft = 100 * 1024, hard = 220 * 1024;
+  const size_t soft = 111 * 1024, hard = 220 * 1024;   // soft: two CTAs per SM
   for (int cl = 1; cl <= 8; cl *= 2) {
     if (cl > P) break;
     const size_t slab = ((size_t)((P + cl - 1) / cl)) * C * es;

@@ -103,19 +103,12 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 
 constexpr int EXP_R = 4;          // image rows per tile
 constexpr int EXP_THREADS = 256;
-constexpr int EXP_G = 4;          // samples staged per barrier phase
-constexpr int EXP_SETS = 2;       // double-buffered staging sets
+constexpr int EXP_WARPS = EXP_THREADS / 32;
 
 __device__ __forceinline__ bool rect_hit(const short* r, int row, int col) {
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     if (row >= r[4 * k] && row < r[4 * k + 1] && col >= r[4 * k + 2] && col < r[4 * k + 3]) return true;
-  return false;
-}
-__device__ __forceinline__ bool rect_rows_hit(const short* r, int r_lo, int r_hi) {
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (r[4 * k] < r_hi && r[4 * k + 1] > r_lo && r[4 * k + 3] > r[4 * k + 2]) return true;
   return false;
 }
 
@@ -125,9 +118,11 @@ struct ExpandParams {
   int B, S, n0, n, H, W, sgroups;
 };
 
-// Shared-memory layout (dynamic): [mbarrier 128 B][rects EXP_G*16 shorts, 128 B][input planes NP*R*W fp32]
-// [clean tile][EXP_SETS*EXP_G staging tiles].  A tile is R full image rows in the output layout
-// (W*CP elements of T per row), i.e. ONE contiguous run of the output tensor -> one bulk store.
+// Shared memory (dynamic): [mbarrier, 512 B][input planes NP*R*W fp32][clean tile R*W*CP T].
+// A tile is R full image rows of the output layout = one contiguous run of the output tensor.
+// Per EOT sample a warp either bulk-stores the clean tile / clean rows (TMA, cp.async.bulk) when no
+// occluder crosses them, or writes an occluded row itself with 16-byte global stores whose keep /
+// zero / mixed status comes from <= 4 element intervals (no staging copy, no block barrier).
 template <typename T, int CP, bool FUSED>
 __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
   constexpr int NP = FUSED ? 7 : 3;
@@ -136,15 +131,15 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
   const int W = p.W, H = p.H, HW = H * W;
   const int tile_px = EXP_R * W;
   const uint32_t plane_bytes = (uint32_t)tile_px * 4u;
-  const uint32_t out_bytes = (uint32_t)tile_px * CP * (uint32_t)sizeof(T);
-  const int row_chunks = W * CP / EPC, tile_chunks = EXP_R * row_chunks;
+  const int row_elems = W * CP;
+  const uint32_t row_bytes = (uint32_t)row_elems * (uint32_t)sizeof(T);
+  const uint32_t out_bytes = row_bytes * EXP_R;
+  const int row_chunks = row_elems / EPC;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-  short* srect_all = reinterpret_cast<short*>(smem + 128);                        // [EXP_SETS][EXP_G][16]
-  int* stouch_all = reinterpret_cast<int*>(smem + 128 + EXP_SETS * EXP_G * 32);  // [EXP_SETS][EXP_G]
   float* in = reinterpret_cast<float*>(smem + 512);
   unsigned char* clean_b = smem + 512 + NP * plane_bytes;
   T* clean = reinterpret_cast<T*>(clean_b);
-  unsigned char* stage_b = clean_b + out_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); ptx::fence_proxy_async(); }
   __syncthreads();
@@ -153,7 +148,6 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
   const int tiles = H / EXP_R;
   const int items = (b_last - b_first + 1) * tiles * p.sgroups;
   uint32_t phase = 0;
-  int set = 0;
 
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int sg = item % p.sgroups;
@@ -165,8 +159,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
     if (s_lo >= s_hi) continue;   // uniform across the CTA
     const int r0 = tile * EXP_R;
 
-    // every bulk store of the previous item must have finished READING the clean tile
-    if (threadIdx.x == 0) ptx::bulk_wait_read<0>();
+    // every warp's bulk stores of the previous item have finished READING the clean tile (see loop end)
     __syncthreads();
     if (threadIdx.x == 0) {
       ptx::mbar_expect_tx(bar, NP * plane_bytes);
@@ -199,84 +192,86 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
     ptx::fence_proxy_async();
     __syncthreads();
 
-    for (int nb = s_lo; nb < s_hi; nb += EXP_G) {
-      const int g_cnt = min(EXP_G, s_hi - nb);
-      short* srect = srect_all + set * EXP_G * 16;     // per-set copies: thread 0 may still be issuing the
-      int* stouch = stouch_all + set * EXP_G;          // previous batch's stores while others run ahead
-      // ---- which samples of this batch have an occluder crossing the tile rows?
-      if (threadIdx.x < g_cnt) {
-        const int g = threadIdx.x;
-        int touch = 0;
-        if (p.rects != nullptr) {
-          const int4* rp = reinterpret_cast<const int4*>(p.rects + (size_t)(nb + g) * 16);
-          const int4 q0 = __ldg(rp), q1 = __ldg(rp + 1);
-          *reinterpret_cast<int4*>(srect + g * 16) = q0;
-          *reinterpret_cast<int4*>(srect + g * 16 + 8) = q1;
-          touch = rect_rows_hit(srect + g * 16, r0, r0 + EXP_R) ? 1 : 0;
-        }
-        stouch[g] = touch;
-      }
-      // the staging set we are about to overwrite was last used two batches ago
-      if (threadIdx.x == 0) ptx::bulk_wait_read<EXP_SETS - 1>();
-      __syncthreads();
-      unsigned char* set_b = stage_b + (size_t)set * EXP_G * out_bytes;
-      // ---- compose the occluded tiles: 16-byte chunks, interval tests per chunk
-      for (int idx = threadIdx.x; idx < g_cnt * tile_chunks; idx += EXP_THREADS) {
-        const int g = idx / tile_chunks, ch = idx % tile_chunks;
-        if (!stouch[g]) continue;
-        const int row = r0 + ch / row_chunks, e0 = (ch % row_chunks) * EPC;
-        const short* r = srect + g * 16;
-        bool zero = false, partial = false;
+    // ---- one warp per EOT sample ---------------------------------------------------------------
+    for (int n = s_lo + warp; n < s_hi; n += EXP_WARPS) {
+      unsigned char* dst = reinterpret_cast<unsigned char*>(p.out) + ((size_t)(n - p.n0) * HW + (size_t)r0 * W) * CP * sizeof(T);
+      int rr0[4], rr1[4], el[4], eh[4];
+      bool any = false;
+      if (p.rects != nullptr) {
+        const int4* rp = reinterpret_cast<const int4*>(p.rects + (size_t)n * 16);
+        const int4 q0 = __ldg(rp), q1 = __ldg(rp + 1);       // same address in every lane: broadcast
+        const int w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (row >= r[4 * k] && row < r[4 * k + 1]) {
-            const int lo_e = r[4 * k + 2] * CP, hi_e = r[4 * k + 3] * CP;
-            if (hi_e > lo_e) {
-              if (e0 >= lo_e && e0 + EPC <= hi_e) zero = true;
-              else if (e0 < hi_e && e0 + EPC > lo_e) partial = true;
+          rr0[k] = (short)(w[2 * k] & 0xffff); rr1[k] = (short)(w[2 * k] >> 16);
+          el[k] = (short)(w[2 * k + 1] & 0xffff) * CP; eh[k] = (short)(w[2 * k + 1] >> 16) * CP;
+          if (eh[k] <= el[k]) { rr0[k] = 0; rr1[k] = 0; }      // empty rectangle
+          any = any || (rr0[k] < r0 + EXP_R && rr1[k] > r0);
+        }
+      }
+      if (!any) {                                               // whole tile untouched: one bulk store
+        if (lane == 0) { ptx::bulk_store(dst, clean_b, out_bytes); ptx::bulk_commit(); }
+        continue;
+      }
+#pragma unroll
+      for (int rr = 0; rr < EXP_R; ++rr) {
+        const int row = r0 + rr;
+        bool cov[4], rany = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { cov[k] = row >= rr0[k] && row < rr1[k]; rany = rany || cov[k]; }
+        if (!rany) {                                            // clean row: bulk store
+          if (lane == 0) { ptx::bulk_store(dst + (size_t)rr * row_bytes, clean_b + (size_t)rr * row_bytes, row_bytes); ptx::bulk_commit(); }
+          continue;
+        }
+        const uint4* crow = reinterpret_cast<const uint4*>(clean_b + (size_t)rr * row_bytes);
+        uint4* drow = reinterpret_cast<uint4*>(dst + (size_t)rr * row_bytes);
+        for (int ch = lane; ch < row_chunks; ch += 32) {
+          const int e0 = ch * EPC;
+          bool zero = false, partial = false;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (cov[k]) {
+              if (e0 >= el[k] && e0 + EPC <= eh[k]) zero = true;
+              else if (e0 < eh[k] && e0 + EPC > el[k]) partial = true;
             }
           }
-        }
-        uint4 v = reinterpret_cast<const uint4*>(clean_b)[ch];
-        if (zero) v = make_uint4(0u, 0u, 0u, 0u);
-        else if (partial) {
-          T* ev = reinterpret_cast<T*>(&v);
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (!zero) {
+            v = crow[ch];
+            if (partial) {
+              T* ev = reinterpret_cast<T*>(&v);
 #pragma unroll
-          for (int k = 0; k < EPC; ++k)
-            if (rect_hit(r, row, (e0 + k) / CP)) ev[k] = from_float<T>(0.f);
+              for (int j = 0; j < EPC; ++j) {
+                bool z = false;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) z = z || (cov[k] && e0 + j >= el[k] && e0 + j < eh[k]);
+                if (z) ev[j] = from_float<T>(0.f);
+              }
+            }
+          }
+          drow[ch] = v;
         }
-        reinterpret_cast<uint4*>(set_b + (size_t)g * out_bytes)[ch] = v;
       }
-      ptx::fence_proxy_async();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        for (int g = 0; g < g_cnt; ++g) {
-          T* dst = reinterpret_cast<T*>(p.out) + ((size_t)(nb + g - p.n0) * HW + (size_t)r0 * W) * CP;
-          ptx::bulk_store(dst, stouch[g] ? (const void*)(set_b + (size_t)g * out_bytes) : (const void*)clean_b, out_bytes);
-        }
-        ptx::bulk_commit();
-      }
-      set ^= 1;
     }
+    // before the clean tile is overwritten: each issuing lane waits for its bulk stores' reads
+    if (lane == 0) ptx::bulk_wait_read<0>();
   }
-  if (threadIdx.x == 0) ptx::bulk_wait_read<0>();
   // (global visibility of the bulk stores is guaranteed at kernel completion)
 }
 
 template <typename T, int CP, bool FUSED>
 static void expand_launch(const ExpandParams& p, int num_sms, cudaStream_t st) {
-  const size_t out_bytes = (size_t)EXP_R * p.W * CP * sizeof(T);
-  const size_t smem = 512 + (size_t)(FUSED ? 7 : 3) * EXP_R * p.W * 4 + (1 + EXP_SETS * EXP_G) * out_bytes;
+  const size_t smem = 512 + (size_t)(FUSED ? 7 : 3) * EXP_R * p.W * 4 + (size_t)EXP_R * p.W * CP * sizeof(T);
   cudaFuncSetAttribute(expand_kernel<T, CP, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ExpandParams q = p;
   const int nb = (p.n0 + p.n - 1) / p.S - p.n0 / p.S + 1;
   const int tiles = p.H / EXP_R;
-  int ctas_per_sm = (int)((220 * 1024) / smem);
+  int ctas_per_sm = (int)((200 * 1024) / smem);
   if (ctas_per_sm < 1) ctas_per_sm = 1;
-  if (ctas_per_sm > 4) ctas_per_sm = 4;
+  if (ctas_per_sm > 6) ctas_per_sm = 6;
   const int target = num_sms * ctas_per_sm;
   int sg = 1;
-  while (nb * tiles * sg < target && sg * EXP_G < p.S && sg < 32) sg *= 2;
+  while (nb * tiles * sg < target && sg * EXP_WARPS < p.S && sg < 32) sg *= 2;
   q.sgroups = sg;
   int grid = nb * tiles * sg;
   if (grid > target) grid = target;
