@@ -447,215 +447,301 @@ __device__ __forceinline__ void cta_group_reduce(const float* a, const float* b,
 }
 }  // namespace gnc
 
+// Persistent variant: a cluster walks samples n = cluster_id, cluster_id + n_clusters, ... and
+// (when two slabs fit) prefetches the next sample's slab with TMA while it normalises the current one.
+namespace gnc {
+struct Pipe {
+  uint64_t* bar;      // [2] mbarriers
+  int nbuf;
+  __device__ __forceinline__ void init() {
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + i)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  // thread 0 only; the buffer's previous generic-proxy readers are behind a __syncthreads
+  __device__ __forceinline__ void issue(void* dst, const void* src, uint32_t bytes, int b) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar + b)), "r"(bytes) : "memory");
+    for (uint32_t off = 0; off < bytes; off += BULK_CHUNK) {
+      const uint32_t nb = bytes - off < BULK_CHUNK ? bytes - off : BULK_CHUNK;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32((const char*)dst + off)),
+                   "l"((const char*)src + off), "r"(nb), "r"(smem_u32(bar + b))
+                   : "memory");
+    }
+  }
+  __device__ __forceinline__ void wait(int b, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(smem_u32(bar + b)), "r"(parity)
+          : "memory");
+    }
+  }
+};
+}  // namespace gnc
+
 template <typename T>
 __global__ void __launch_bounds__(gnc::THREADS) gn_fwd_cluster_kernel(const T* __restrict__ x, T* __restrict__ y,
                                                                        const float* __restrict__ gamma,
                                                                        const float* __restrict__ beta,
-                                                                       float* __restrict__ stats, int P, int C) {
+                                                                       float* __restrict__ stats, int N, int P, int C,
+                                                                       int nbuf, uint32_t slab_stride) {
   constexpr int V = Vec<T>::N;
   extern __shared__ __align__(128) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
-  const int n = blockIdx.x / CL;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+  gnc::Pipe pipe{reinterpret_cast<uint64_t*>(smem), nbuf};
   float* part = reinterpret_cast<float*>(smem + 64);          // [32][2] this CTA's partials
   float* s_mean = reinterpret_cast<float*>(smem + 64 + 256);  // [32]
   float* s_rstd = s_mean + GN_GROUPS;                         // [32]
   float* tp = reinterpret_cast<float*>(smem + gnc::HDR);
-  T* slab = reinterpret_cast<T*>(smem + gnc::HDR + gnc::TP_BYTES);
+  unsigned char* slabs = smem + gnc::HDR + gnc::TP_BYTES;
 
   const int p0 = (int)(((long long)P * rank) / CL), p1 = (int)(((long long)P * (rank + 1)) / CL);
   const int rows = p1 - p0;
-  const T* src = x + ((size_t)n * P + p0) * C;
-  gnc::slab_load(slab, src, (uint32_t)((size_t)rows * C * sizeof(T)), bar);
-  gnc::slab_wait(bar);
-
+  const uint32_t slab_bytes = (uint32_t)((size_t)rows * C * sizeof(T));
   const int cols = C / V, rpi = gnc::THREADS / cols, cpg = C / GN_GROUPS;
   const int tcol = threadIdx.x % cols, trow = threadIdx.x / cols;
-  float a[V], b[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) { a[i] = 0.f; b[i] = 0.f; }
-  for (int r = trow; r < rows; r += rpi) {
-    Vec<T> v; v.load(slab + (size_t)r * C + tcol * V);
-    float f[V]; v.unpack(f);
-#pragma unroll
-    for (int i = 0; i < V; ++i) { a[i] += f[i]; b[i] = fmaf(f[i], f[i], b[i]); }
-  }
-  gnc::cta_group_reduce<V>(a, b, C, tp, part);
-  cluster.sync();
-  if (threadIdx.x < GN_GROUPS) {
-    float s = 0.f, q = 0.f;
-    for (int r = 0; r < CL; ++r) {
-      const float* rp = cluster.map_shared_rank(part, r);
-      s += rp[threadIdx.x * 2 + 0];
-      q += rp[threadIdx.x * 2 + 1];
+  pipe.init();
+
+  int it = 0;
+  for (int n = cluster_id; n < N; n += n_clusters, ++it) {
+    const int b = nbuf == 2 ? (it & 1) : 0;
+    const uint32_t parity = nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
+    if (threadIdx.x == 0) {
+      if (it == 0 || nbuf == 1) pipe.issue(slabs + (size_t)b * slab_stride, x + ((size_t)n * P + p0) * C, slab_bytes, b);
+      if (nbuf == 2 && n + n_clusters < N)
+        pipe.issue(slabs + (size_t)(b ^ 1) * slab_stride, x + ((size_t)(n + n_clusters) * P + p0) * C, slab_bytes, b ^ 1);
     }
-    const float cnt = (float)P * cpg;
-    const float mean = s / cnt;
-    float var = q / cnt - mean * mean;
-    var = var < 0.f ? 0.f : var;
-    const float rstd = rsqrtf(var + 1e-5f);
-    s_mean[threadIdx.x] = mean;
-    s_rstd[threadIdx.x] = rstd;
-    if (rank == 0) {
-      stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 0] = mean;
-      stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 1] = rstd;
+    const T* slab = reinterpret_cast<const T*>(slabs + (size_t)b * slab_stride);
+    pipe.wait(b, parity);
+
+    float a[V], bq[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { a[i] = 0.f; bq[i] = 0.f; }
+    for (int r = trow; r < rows; r += rpi) {
+      Vec<T> v; v.load(slab + (size_t)r * C + tcol * V);
+      float f[V]; v.unpack(f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { a[i] += f[i]; bq[i] = fmaf(f[i], f[i], bq[i]); }
     }
-  }
-  __syncthreads();
-  cluster.barrier_arrive();   // our remote reads are done; peers may exit once everyone has arrived
-  float sa[V], sb[V];
+    gnc::cta_group_reduce<V>(a, bq, C, tp, part);
+    cluster.sync();
+    if (threadIdx.x < GN_GROUPS) {
+      float s = 0.f, q = 0.f;
+      for (int r = 0; r < CL; ++r) {
+        const float* rp = cluster.map_shared_rank(part, r);
+        s += rp[threadIdx.x * 2 + 0];
+        q += rp[threadIdx.x * 2 + 1];
+      }
+      const float cnt = (float)P * cpg;
+      const float mean = s / cnt;
+      float var = q / cnt - mean * mean;
+      var = var < 0.f ? 0.f : var;
+      const float rstd = rsqrtf(var + 1e-5f);
+      s_mean[threadIdx.x] = mean;
+      s_rstd[threadIdx.x] = rstd;
+      if (rank == 0) {
+        stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 0] = mean;
+        stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 1] = rstd;
+      }
+    }
+    __syncthreads();
+    cluster.barrier_arrive();   // our remote reads are done
+    float sa[V], sb[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int c = tcol * V + i, g = c / cpg;
-    sa[i] = s_rstd[g] * gamma[c];
-    sb[i] = beta[c] - s_mean[g] * sa[i];
-  }
-  T* dst = y + ((size_t)n * P + p0) * C;
-  for (int r = trow; r < rows; r += rpi) {
-    Vec<T> v; v.load(slab + (size_t)r * C + tcol * V);
-    float f[V]; v.unpack(f);
+    for (int i = 0; i < V; ++i) {
+      const int c = tcol * V + i, g = c / cpg;
+      sa[i] = s_rstd[g] * gamma[c];
+      sb[i] = beta[c] - s_mean[g] * sa[i];
+    }
+    T* dst = y + ((size_t)n * P + p0) * C;
+    for (int r = trow; r < rows; r += rpi) {
+      Vec<T> v; v.load(slab + (size_t)r * C + tcol * V);
+      float f[V]; v.unpack(f);
 #pragma unroll
-    for (int i = 0; i < V; ++i) f[i] = fmaxf(fmaf(sa[i], f[i], sb[i]), 0.f);
-    v.pack(f); v.store(dst + (size_t)r * C + tcol * V);
+      for (int i = 0; i < V; ++i) f[i] = fmaxf(fmaf(sa[i], f[i], sb[i]), 0.f);
+      v.pack(f); v.store(dst + (size_t)r * C + tcol * V);
+    }
+    __syncthreads();            // slab b, tp, s_mean free for the next iteration
+    cluster.barrier_wait();     // every peer has read our partials: `part` may be rewritten / we may exit
   }
-  cluster.barrier_wait();   // nobody leaves while a peer may still read its partials
 }
 
-template <typename T>
-__global__ void __launch_bounds__(gnc::THREADS) gn_bwd_cluster_kernel(const T* __restrict__ dy, const T* __restrict__ x,
-                                                                       const T* __restrict__ addend, T* __restrict__ dx,
-                                                                       const float* __restrict__ gamma,
-                                                                       const float* __restrict__ beta,
-                                                                       const float* __restrict__ stats, int P, int C) {
+// UG: all V channels of a thread share one GroupNorm group (cpg >= V) -> per-group scalars
+template <typename T, bool UG>
+__global__ void __launch_bounds__(gnc::THREADS, 2) gn_bwd_cluster_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                          const T* __restrict__ addend, T* __restrict__ dx,
+                                                                          const float* __restrict__ gamma,
+                                                                          const float* __restrict__ beta,
+                                                                          const float* __restrict__ stats, int N, int P, int C,
+                                                                          int nbuf, uint32_t slab_stride) {
   constexpr int V = Vec<T>::N;
+  constexpr int U = 2;          // independent global loads in flight per thread (plus the TMA prefetch)
+  constexpr int GV = UG ? 1 : V;
   extern __shared__ __align__(128) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
-  const int n = blockIdx.x / CL;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+  gnc::Pipe pipe{reinterpret_cast<uint64_t*>(smem), nbuf};
   float* part = reinterpret_cast<float*>(smem + 64);
   float* s_1 = reinterpret_cast<float*>(smem + 64 + 256);
   float* s_2 = s_1 + GN_GROUPS;
   float* tp = reinterpret_cast<float*>(smem + gnc::HDR);
-  T* slab = reinterpret_cast<T*>(smem + gnc::HDR + gnc::TP_BYTES);
+  unsigned char* slabs = smem + gnc::HDR + gnc::TP_BYTES;
 
   const int p0 = (int)(((long long)P * rank) / CL), p1 = (int)(((long long)P * (rank + 1)) / CL);
   const int rows = p1 - p0;
-  const size_t base = ((size_t)n * P + p0) * C;
-  gnc::slab_load(slab, x + base, (uint32_t)((size_t)rows * C * sizeof(T)), bar);
-
+  const uint32_t slab_bytes = (uint32_t)((size_t)rows * C * sizeof(T));
   const int cols = C / V, rpi = gnc::THREADS / cols, cpg = C / GN_GROUPS;
   const int tcol = threadIdx.x % cols, trow = threadIdx.x / cols;
-  float ga[V], sa[V], sb[V], mu[V], rs[V];
+  float ga[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int c = tcol * V + i, g = c / cpg;
-    ga[i] = gamma[c];
-    mu[i] = stats[((size_t)n * GN_GROUPS + g) * 2 + 0];
-    rs[i] = stats[((size_t)n * GN_GROUPS + g) * 2 + 1];
-    sa[i] = rs[i] * ga[i];
-    sb[i] = beta[c] - mu[i] * sa[i];
-  }
-  gnc::slab_wait(bar);
-  float a[V], b[V];
+  for (int i = 0; i < V; ++i) ga[i] = gamma[tcol * V + i];
+  pipe.init();
+
+  int it = 0;
+  for (int n = cluster_id; n < N; n += n_clusters, ++it) {
+    const int b = nbuf == 2 ? (it & 1) : 0;
+    const uint32_t parity = nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
+    const size_t base = ((size_t)n * P + p0) * C;
+    if (threadIdx.x == 0) {
+      if (it == 0 || nbuf == 1) pipe.issue(slabs + (size_t)b * slab_stride, x + base, slab_bytes, b);
+      if (nbuf == 2 && n + n_clusters < N)
+        pipe.issue(slabs + (size_t)(b ^ 1) * slab_stride, x + ((size_t)(n + n_clusters) * P + p0) * C, slab_bytes, b ^ 1);
+    }
+    const T* slab = reinterpret_cast<const T*>(slabs + (size_t)b * slab_stride);
+    float sa[V], sb[V], mu[GV], rs[GV];
 #pragma unroll
-  for (int i = 0; i < V; ++i) { a[i] = 0.f; b[i] = 0.f; }
-  constexpr int U = 4;   // independent global loads in flight per thread
-  for (int r0 = trow; r0 < rows; r0 += rpi * U) {
-    Vec<T> vd[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int r = r0 + u * rpi;
-      if (r < rows) vd[u].load(dy + base + (size_t)r * C + tcol * V);
+    for (int i = 0; i < GV; ++i) {
+      const int g = (tcol * V + i) / cpg;
+      mu[i] = stats[((size_t)n * GN_GROUPS + g) * 2 + 0];
+      rs[i] = stats[((size_t)n * GN_GROUPS + g) * 2 + 1];
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int r = r0 + u * rpi;
-      if (r < rows) {
-        Vec<T> vx; vx.load(slab + (size_t)r * C + tcol * V);
-        float fx[V], fd[V]; vx.unpack(fx); vd[u].unpack(fd);
+    for (int i = 0; i < V; ++i) {
+      sa[i] = rs[UG ? 0 : i] * ga[i];
+      sb[i] = beta[tcol * V + i] - mu[UG ? 0 : i] * sa[i];
+    }
+    pipe.wait(b, parity);
+    float a[V], bq[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          const float pre = fmaf(sa[i], fx[i], sb[i]);
-          const float dg = pre > 0.f ? fd[i] * ga[i] : 0.f;
-          const float xh = (fx[i] - mu[i]) * rs[i];
-          a[i] += dg; b[i] = fmaf(dg, xh, b[i]);
+    for (int i = 0; i < V; ++i) { a[i] = 0.f; bq[i] = 0.f; }
+    for (int r0 = trow; r0 < rows; r0 += rpi * U) {
+      Vec<T> vd[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = r0 + u * rpi;
+        if (r < rows) vd[u].load(dy + base + (size_t)r * C + tcol * V);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = r0 + u * rpi;
+        if (r < rows) {
+          Vec<T> vx; vx.load(slab + (size_t)r * C + tcol * V);
+          float fx[V], fd[V]; vx.unpack(fx); vd[u].unpack(fd);
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const float pre = fmaf(sa[i], fx[i], sb[i]);
+            const float dg = pre > 0.f ? fd[i] * ga[i] : 0.f;
+            const float xh = (fx[i] - mu[UG ? 0 : i]) * rs[UG ? 0 : i];
+            a[i] += dg; bq[i] = fmaf(dg, xh, bq[i]);
+          }
         }
       }
     }
-  }
-  gnc::cta_group_reduce<V>(a, b, C, tp, part);
-  cluster.sync();
-  if (threadIdx.x < GN_GROUPS) {
-    float s = 0.f, q = 0.f;
-    for (int r = 0; r < CL; ++r) {
-      const float* rp = cluster.map_shared_rank(part, r);
-      s += rp[threadIdx.x * 2 + 0];
-      q += rp[threadIdx.x * 2 + 1];
+    gnc::cta_group_reduce<V>(a, bq, C, tp, part);
+    cluster.sync();
+    if (threadIdx.x < GN_GROUPS) {
+      float s = 0.f, q = 0.f;
+      for (int r = 0; r < CL; ++r) {
+        const float* rp = cluster.map_shared_rank(part, r);
+        s += rp[threadIdx.x * 2 + 0];
+        q += rp[threadIdx.x * 2 + 1];
+      }
+      const float inv_m = 1.0f / ((float)P * cpg);
+      s_1[threadIdx.x] = s * inv_m;
+      s_2[threadIdx.x] = q * inv_m;
     }
-    const float inv_m = 1.0f / ((float)P * cpg);
-    s_1[threadIdx.x] = s * inv_m;
-    s_2[threadIdx.x] = q * inv_m;
-  }
-  __syncthreads();
-  cluster.barrier_arrive();
-  float m1[V], m2[V];
+    __syncthreads();
+    cluster.barrier_arrive();
+    float m1[GV], m2[GV];
 #pragma unroll
-  for (int i = 0; i < V; ++i) { const int g = (tcol * V + i) / cpg; m1[i] = s_1[g]; m2[i] = s_2[g]; }
-  for (int r0 = trow; r0 < rows; r0 += rpi * U) {
-    Vec<T> vd[U], va[U];
+    for (int i = 0; i < GV; ++i) { const int g = (tcol * V + i) / cpg; m1[i] = s_1[g]; m2[i] = s_2[g]; }
+    for (int r0 = trow; r0 < rows; r0 += rpi * U) {
+      Vec<T> vd[U], va[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int r = r0 + u * rpi;
-      if (r < rows) {
-        const size_t off = base + (size_t)r * C + tcol * V;
-        vd[u].load(dy + off);
-        if (addend != nullptr) va[u].load(addend + off);
+      for (int u = 0; u < U; ++u) {
+        const int r = r0 + u * rpi;
+        if (r < rows) {
+          const size_t off = base + (size_t)r * C + tcol * V;
+          vd[u].load(dy + off);
+          if (addend != nullptr) va[u].load(addend + off);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = r0 + u * rpi;
+        if (r < rows) {
+          const size_t off = base + (size_t)r * C + tcol * V;
+          Vec<T> vx; vx.load(slab + (size_t)r * C + tcol * V);
+          float fx[V], fd[V], fo[V]; vx.unpack(fx); vd[u].unpack(fd);
+          if (addend != nullptr) va[u].unpack(fo);
+          else {
+#pragma unroll
+            for (int i = 0; i < V; ++i) fo[i] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const float pre = fmaf(sa[i], fx[i], sb[i]);
+            const float dg = pre > 0.f ? fd[i] * ga[i] : 0.f;
+            const float xh = (fx[i] - mu[UG ? 0 : i]) * rs[UG ? 0 : i];
+            fo[i] += rs[UG ? 0 : i] * (dg - m1[UG ? 0 : i] - xh * m2[UG ? 0 : i]);
+          }
+          Vec<T> vo; vo.pack(fo); vo.store(dx + off);
+        }
       }
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int r = r0 + u * rpi;
-      if (r < rows) {
-        const size_t off = base + (size_t)r * C + tcol * V;
-        Vec<T> vx; vx.load(slab + (size_t)r * C + tcol * V);
-        float fx[V], fd[V], fo[V]; vx.unpack(fx); vd[u].unpack(fd);
-        if (addend != nullptr) va[u].unpack(fo);
-        else {
-#pragma unroll
-          for (int i = 0; i < V; ++i) fo[i] = 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          const float pre = fmaf(sa[i], fx[i], sb[i]);
-          const float dg = pre > 0.f ? fd[i] * ga[i] : 0.f;
-          const float xh = (fx[i] - mu[i]) * rs[i];
-          fo[i] += rs[i] * (dg - m1[i] - xh * m2[i]);
-        }
-        Vec<T> vo; vo.pack(fo); vo.store(dx + off);
-      }
-    }
+    __syncthreads();
+    cluster.barrier_wait();
   }
-  cluster.barrier_wait();
 }
 
-// cluster size for a [P, C] sample of element size es: smallest power of two whose slab fits the
-// per-CTA budget (two CTAs per SM when possible); 0 = does not fit -> two-pass fallback.
-static int gn_cluster_size(int P, int C, size_t es, size_t* smem_out) {
+struct GnPlan { int cl; int nbuf; size_t smem; uint32_t slab_stride; int ctas_per_sm; };
+static bool gn_plan(int P, int C, size_t es, GnPlan* out) {
   static int mode = -1;
   if (mode < 0) { const char* e = getenv("DORPATCH_GN"); mode = (e && strcmp(e, "twopass") == 0) ? 0 : 1; }
-  if (!mode) return 0;
-  if (C / (int)(16 / es) > gnc::THREADS) return 0;
-  const size_t total = (size_t)P * C * es, fixed = gnc::HDR + gnc::TP_BYTES;
-  const size_t soft = 111 * 1024, hard = 220 * 1024;   // soft: two CTAs per SM
+  if (!mode) return false;
+  if (C / (int)(16 / es) > gnc::THREADS) return false;
+  const size_t fixed = gnc::HDR + gnc::TP_BYTES;
+  const size_t budget2 = 111 * 1024, budget1 = 220 * 1024;   // smem per CTA for two / one CTA per SM
   for (int cl = 1; cl <= 8; cl *= 2) {
     if (cl > P) break;
-    const size_t slab = ((size_t)((P + cl - 1) / cl)) * C * es;
-    if (slab + fixed <= soft || (cl == 8 && slab + fixed <= hard)) { *smem_out = slab + fixed; return cl; }
+    const size_t slab = (((size_t)((P + cl - 1) / cl)) * C * es + 127) / 128 * 128;
+    if (fixed + 2 * slab <= budget2) { *out = GnPlan{cl, 2, fixed + 2 * slab, (uint32_t)slab, 2}; return true; }
+    if (cl == 8) {
+      if (fixed + 2 * slab <= budget1) { *out = GnPlan{cl, 2, fixed + 2 * slab, (uint32_t)slab, 1}; return true; }
+      if (fixed + slab <= budget1) { *out = GnPlan{cl, 1, fixed + slab, (uint32_t)slab, 1}; return true; }
+    }
   }
-  (void)total;
-  return 0;
+  return false;
+}
+static int g_num_sms = 0;
+static int gn_grid(const GnPlan& pl, int N) {
+  if (g_num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  int n_clusters = (g_num_sms * pl.ctas_per_sm) / pl.cl;
+  if (n_clusters < 1) n_clusters = 1;
+  if (n_clusters > N) n_clusters = N;
+  return n_clusters * pl.cl;
 }
 
 template <typename K, typename... Args>
@@ -908,12 +994,12 @@ void launch_subsample2_adjoint_add(const void* dy, void* dx, int N, int H, int W
 
 void launch_gn_relu_forward(const void* x, void* y, const float* gamma, const float* beta, float* partial,
                             float* stats, int N, int P, int C, bool bf16, cudaStream_t st) {
-  size_t smem = 0;
-  const int cl = gn_cluster_size(P, C, bf16 ? 2 : 4, &smem);
-  if (cl > 0) {
+  GnPlan pl;
+  if (gn_plan(P, C, bf16 ? 2 : 4, &pl)) {
+    const int grid = gn_grid(pl, N);
     bool ok;
-    if (bf16) ok = launch_cluster(gn_fwd_cluster_kernel<__nv_bfloat16>, cl, cl * N, smem, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, stats, P, C);
-    else ok = launch_cluster(gn_fwd_cluster_kernel<float>, cl, cl * N, smem, st, (const float*)x, (float*)y, gamma, beta, stats, P, C);
+    if (bf16) ok = launch_cluster(gn_fwd_cluster_kernel<__nv_bfloat16>, pl.cl, grid, pl.smem, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, stats, N, P, C, pl.nbuf, pl.slab_stride);
+    else ok = launch_cluster(gn_fwd_cluster_kernel<float>, pl.cl, grid, pl.smem, st, (const float*)x, (float*)y, gamma, beta, stats, N, P, C, pl.nbuf, pl.slab_stride);
     if (ok) return;
     cudaGetLastError();   // clear and fall back
   }
@@ -923,12 +1009,15 @@ void launch_gn_relu_forward(const void* x, void* y, const float* gamma, const fl
 void launch_gn_relu_backward(const void* dy, const void* x, const void* addend, void* dx, const float* gamma,
                              const float* beta, const float* stats, float* partial, int N, int P, int C, bool bf16,
                              cudaStream_t st) {
-  size_t smem = 0;
-  const int cl = gn_cluster_size(P, C, bf16 ? 2 : 4, &smem);
-  if (cl > 0) {
+  GnPlan pl;
+  if (gn_plan(P, C, bf16 ? 2 : 4, &pl)) {
+    const int grid = gn_grid(pl, N);
     bool ok;
-    if (bf16) ok = launch_cluster(gn_bwd_cluster_kernel<__nv_bfloat16>, cl, cl * N, smem, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)addend, (__nv_bfloat16*)dx, gamma, beta, stats, P, C);
-    else ok = launch_cluster(gn_bwd_cluster_kernel<float>, cl, cl * N, smem, st, (const float*)dy, (const float*)x, (const float*)addend, (float*)dx, gamma, beta, stats, P, C);
+    const bool ug = (C / GN_GROUPS) >= (bf16 ? 8 : 4);
+#define GNB(TT, UGV) launch_cluster(gn_bwd_cluster_kernel<TT, UGV>, pl.cl, grid, pl.smem, st, (const TT*)dy, (const TT*)x, (const TT*)addend, (TT*)dx, gamma, beta, stats, N, P, C, pl.nbuf, pl.slab_stride)
+    if (bf16) ok = ug ? GNB(__nv_bfloat16, true) : GNB(__nv_bfloat16, false);
+    else ok = ug ? GNB(float, true) : GNB(float, false);
+#undef GNB
     if (ok) return;
     cudaGetLastError();
   }
