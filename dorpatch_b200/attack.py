@@ -177,7 +177,9 @@ class DorPatch(object):
     def generate(self, model, x, patch_budget, n_classes, save_dir, batch_id, y=None, targeted=False,
                  lr=1e-2, confidence=1e-1, clip_min=0, clip_max=1, max_iterations=5000, basic_unit=7,
                  selection='topk', dropout=2, sampling_size=128, density=1e-3, structured=1e-3, eps=4., dual=False,
-                 **kwargs):
+                 eot_affine=0.0, eot_colour=0.0, eot_seed=0, **kwargs):
+        """Reference signature (attack.py:51-53) plus three opt-in keywords for the affine / colour
+        EOT extension (default 0 = off = the reference's behaviour)."""
         if basic_unit != 7:
             raise NotImplementedError("the native kernels are built for basic_unit=7")
         if selection != 'topk':
@@ -221,6 +223,8 @@ class DorPatch(object):
         st = [_ImageState(lr, structured, y[b], targeted, rngs[b]) for b in range(B)]
         dir_0 = os.path.dirname(save_dir.rstrip('/')) if save_dir else None
         G = torch.zeros_like(x)
+        use_eot = (eot_affine != 0.0) or (eot_colour != 0.0)
+        eot_rng = np.random.RandomState(eot_seed)
         # Reference quirk: an early-stop `break` in stage 0 (attack.py:310-315) skips
         # `adv_pattern.grad.zero_()` (:342), so the first stage-1 backward accumulates onto the
         # gradient of the last stage-0 iteration.  Kept per image, zero unless stage 0 stopped early.
@@ -293,8 +297,12 @@ class DorPatch(object):
                 rects = _masks.gather(table, idx[:, sl], idx2[:, sl] if dual else None)
                 structured_used = [s.structured for s in st]
                 coeff_used = [s.coeff_group_lasso for s in st]
+                xf = None
+                if use_eot:
+                    from . import eot as _eot
+                    xf = _eot.sample(eot_rng, B, S, eot_affine, eot_colour)[:, sl]
                 r = eng.attack_grad(x, adv_mask, adv_pattern, rects, [s.y for s in st],
-                                    [s.crit_targeted for s in st], confidence, eps, stage, G, S_total=S)
+                                    [s.crit_targeted for s in st], confidence, eps, stage, G, S_total=S, xforms=xf)
                 loss_adv, preds = r["loss_adv"], r["preds"]
                 if dist:                                         # one all-reduce of the patch gradient per step
                     loss_adv, preds = exchange_shards(dist, G, loss_adv, preds)

@@ -146,7 +146,7 @@ struct dp_engine {
   // per-sample buffers (grown on demand)
   int cap_samples = 0;
   int16_t* rects_d = nullptr; int32_t* y_d = nullptr; uint8_t* tg_d = nullptr;
-  float* loss_d = nullptr; int32_t* preds_d = nullptr;
+  float* loss_d = nullptr; int32_t* preds_d = nullptr; float* xf_d = nullptr;
   // pinned staging
   unsigned char* pin = nullptr; size_t pin_bytes = 0;
 
@@ -215,6 +215,7 @@ struct dp_engine {
     tg_d = (uint8_t*)dmalloc((size_t)cap_samples);
     loss_d = (float*)dmalloc((size_t)cap_samples * sizeof(float));
     preds_d = (int32_t*)dmalloc((size_t)cap_samples * sizeof(int32_t));
+    xf_d = (float*)dmalloc((size_t)cap_samples * 8 * sizeof(float));
   }
 
   // ---- geometry -----------------------------------------------------------------------
@@ -853,7 +854,8 @@ static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t
   // per-sample labels / criterion flags / rectangles -> device.  Pinned staging layout:
   // [H2D region: ys | tg | rects][D2H region: results]; the regions never overlap.
   const size_t rect_bytes = a->rects_host ? (size_t)N * 16 * sizeof(int16_t) : 0;
-  const size_t h2d_bytes = (((size_t)N * 5 + 15) / 16) * 16 + rect_bytes;
+  const size_t xf_bytes = a->xform_host ? (size_t)N * 8 * sizeof(float) : 0;
+  const size_t h2d_bytes = (((size_t)N * 5 + 15) / 16) * 16 + rect_bytes + xf_bytes;
   const size_t d2h_off = (h2d_bytes + 255) / 256 * 256;
   e->ensure_pin(d2h_off + (size_t)N * 8 + (size_t)B * 16 + 512);
   int32_t* ys = (int32_t*)e->pin;
@@ -867,6 +869,12 @@ static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t
   CUDA_OK(cudaMemcpyAsync(e->y_d, ys, (size_t)N * 4, cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemcpyAsync(e->tg_d, tg, (size_t)N, cudaMemcpyHostToDevice, st));
   if (rect_bytes) CUDA_OK(cudaMemcpyAsync(e->rects_d, rp, rect_bytes, cudaMemcpyHostToDevice, st));
+  if (xf_bytes) {
+    unsigned char* xp = rp + rect_bytes;
+    memcpy(xp, a->xform_host, xf_bytes);
+    CUDA_OK(cudaMemcpyAsync(e->xf_d, xp, xf_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemsetAsync(a->grad_adv, 0, (size_t)B * 3 * H * H * sizeof(float), st));   // the adjoint scatters with atomics
+  }
   const int16_t* rects = rect_bytes ? e->rects_d : nullptr;
 
   const double img_bytes = (double)B * H * H * 4;
@@ -878,16 +886,27 @@ static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t
   const float inv_s = 1.0f / (float)a->S_total;
   for (int n0 = 0; n0 < N; n0 += e->chunk) {
     const int n = std::min(e->chunk, N - n0);
-    PROF(e, "expand_k1", (double)n * H * H * 3 * e->es + 7.0 * H * H * 4 * (double)n / S, 0, st,
-         dp::launch_expand(nullptr, a->x, a->mask, a->pattern, e->scale, rects, e->net_in, B, S, n0, n, H, H, e->Cp, e->bf16, true, e->num_sms, st));
+    if (xf_bytes) {
+      PROF(e, "expand_affine", (double)n * H * H * 3 * e->es + 3.0 * H * H * 4 * (double)n / S, 0, st,
+           dp::launch_expand_affine(e->adv_x, e->xf_d, rects, e->net_in, S, n0, n, H, H, e->Cp, e->bf16, st));
+    } else {
+      PROF(e, "expand_k1", (double)n * H * H * 3 * e->es + 7.0 * H * H * 4 * (double)n / S, 0, st,
+           dp::launch_expand(nullptr, a->x, a->mask, a->pattern, e->scale, rects, e->net_in, B, S, n0, n, H, H, e->Cp, e->bf16, true, e->num_sms, st));
+    }
     KERNEL_OK(); ++e->launches;
     e->forward(n, e->net_in, true, st);
     PROF(e, "cw_k4", 2.0 * n * e->K * 4, 0, st,
          dp::launch_cw(e->logits, e->y_d + n0, e->tg_d + n0, a->confidence, inv_s, e->loss_d + n0, e->preds_d + n0, e->dlogits, n, e->K, st));
     KERNEL_OK(); ++e->launches;
     e->backward(n, e->dlogits, st);
-    PROF(e, "reduce_k1t", (double)n * H * H * 3 * e->es + 3.0 * H * H * 4 * (double)n / S, 0, st,
-         dp::launch_reduce(e->d_input, rects, a->grad_adv, B, S, n0, n, H, H, e->Cpd, e->bf16, st)); KERNEL_OK(); ++e->launches;
+    if (xf_bytes) {
+      PROF(e, "reduce_affine", (double)n * H * H * 3 * e->es + 3.0 * H * H * 4 * (double)n / S, 0, st,
+           dp::launch_reduce_affine(e->d_input, e->adv_x, e->xf_d, rects, a->grad_adv, S, n0, n, H, H, e->Cpd, e->bf16, st));
+    } else {
+      PROF(e, "reduce_k1t", (double)n * H * H * 3 * e->es + 3.0 * H * H * 4 * (double)n / S, 0, st,
+           dp::launch_reduce(e->d_input, rects, a->grad_adv, B, S, n0, n, H, H, e->Cpd, e->bf16, st));
+    }
+    KERNEL_OK(); ++e->launches;
   }
   // results -> host (pinned staging, one sync)
   unsigned char* out = e->pin + d2h_off;

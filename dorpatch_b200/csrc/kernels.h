@@ -59,6 +59,11 @@ void launch_paste(const float* x, const float* mask, const float* pattern, float
 void launch_expand(const float* img, const float* x, const float* mask, const float* pattern, const float* scale,
                    const int16_t* rects, void* out, int B, int S, int n0, int n, int H, int W, int Cp, bool bf16,
                    bool fused, int num_sms, cudaStream_t st);
+// optional affine / colour EOT (gather) and its adjoint (atomic scatter into a zeroed G); xf [N][8] dev
+void launch_expand_affine(const float* adv, const float* xf, const int16_t* rects, void* out, int S, int n0, int n,
+                          int H, int W, int Cp, bool bf16, cudaStream_t st);
+void launch_reduce_affine(const void* dz, const float* adv, const float* xf, const int16_t* rects, float* G, int S, int n0,
+                          int n, int H, int W, int Cp, bool bf16, cudaStream_t st);
 // K4: CW loss, argmax, dlogits (scaled by inv_s_total).  y/targeted are per-sample dev arrays.
 void launch_cw(const float* logits, const int32_t* y, const uint8_t* targeted, float confidence, float inv_s_total,
                float* loss, int32_t* preds, float* dlogits, int N, int K, cudaStream_t st);

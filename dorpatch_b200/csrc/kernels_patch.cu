@@ -298,6 +298,112 @@ void launch_expand(const float* img, const float* x, const float* mask, const fl
 }
 
 // =====================================================================================
+// Optional affine / colour EOT (named by the north-star, absent from the reference --
+// default off).  Per sample: bilinear warp of the pasted image by theta (torch affine_grid /
+// grid_sample semantics: align_corners=False, padding_mode='border'), then
+// v' = clamp(contrast*(v-0.5)+0.5+brightness, 0, 1), then occlusion + normalisation.
+// xf[n] = {t00,t01,t02,t10,t11,t12, contrast, brightness}.  Gather kernel (the source rows are
+// arbitrary, so no TMA row tiles); its adjoint scatters with fp32 atomics.
+// =====================================================================================
+struct AffTap { int i00, i01, i10, i11; float w00, w01, w10, w11; };
+__device__ __forceinline__ AffTap affine_taps(const float* __restrict__ t, int h, int w, int H, int W) {
+  const float xn = (2.f * w + 1.f) / W - 1.f, yn = (2.f * h + 1.f) / H - 1.f;
+  float fx = ((t[0] * xn + t[1] * yn + t[2] + 1.f) * W - 1.f) * 0.5f;
+  float fy = ((t[3] * xn + t[4] * yn + t[5] + 1.f) * H - 1.f) * 0.5f;
+  fx = fminf(fmaxf(fx, 0.f), (float)(W - 1));
+  fy = fminf(fmaxf(fy, 0.f), (float)(H - 1));
+  const int x0 = (int)floorf(fx), y0 = (int)floorf(fy);
+  const float ax = fx - x0, ay = fy - y0;
+  const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+  AffTap a;
+  a.i00 = y0 * W + x0; a.i01 = y0 * W + x1; a.i10 = y1 * W + x0; a.i11 = y1 * W + x1;
+  a.w00 = (1.f - ax) * (1.f - ay); a.w01 = (x0 + 1 < W ? ax : 0.f) * (1.f - ay);
+  a.w10 = (1.f - ax) * (y0 + 1 < H ? ay : 0.f); a.w11 = (x0 + 1 < W ? ax : 0.f) * (y0 + 1 < H ? ay : 0.f);
+  return a;
+}
+
+template <typename T, int CP>
+__global__ void __launch_bounds__(256) expand_affine_kernel(const float* __restrict__ adv, const float* __restrict__ xf,
+                                                            const int16_t* __restrict__ rects, T* __restrict__ out,
+                                                            int S, int n0, int H, int W) {
+  const int HW = H * W, n = n0 + blockIdx.y, b = n / S;
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= HW) return;
+  const int h = px / W, w = px % W;
+  const float* t = xf + (size_t)n * 8;
+  const AffTap a = affine_taps(t, h, w, H, W);
+  bool occ = false;
+  if (rects != nullptr) {
+    short r[16];
+    const int4* rp = reinterpret_cast<const int4*>(rects + (size_t)n * 16);
+    *reinterpret_cast<int4*>(r) = __ldg(rp); *reinterpret_cast<int4*>(r + 8) = __ldg(rp + 1);
+    occ = rect_hit(r, h, w);
+  }
+  T* o = out + ((size_t)blockIdx.y * HW + px) * CP;
+#pragma unroll
+  for (int c = 0; c < CP; ++c) {
+    float z = 0.f;
+    if (c < 3 && !occ) {
+      const float* pl = adv + ((size_t)b * 3 + c) * HW;
+      float v = a.w00 * pl[a.i00] + a.w01 * pl[a.i01] + a.w10 * pl[a.i10] + a.w11 * pl[a.i11];
+      v = fminf(fmaxf(t[6] * (v - 0.5f) + 0.5f + t[7], 0.f), 1.f);
+      z = (v - 0.5f) * 2.f;
+    }
+    o[c] = from_float<T>(z);
+  }
+}
+
+// adjoint: G[b] += scatter( 2 * keep * contrast * [0 < v' < 1] * dz[n] ); G must be zero-initialised
+template <typename T, int CP>
+__global__ void __launch_bounds__(256) reduce_affine_kernel(const T* __restrict__ dz, const float* __restrict__ adv,
+                                                            const float* __restrict__ xf, const int16_t* __restrict__ rects,
+                                                            float* __restrict__ G, int S, int n0, int H, int W) {
+  const int HW = H * W, n = n0 + blockIdx.y, b = n / S;
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= HW) return;
+  const int h = px / W, w = px % W;
+  if (rects != nullptr) {
+    short r[16];
+    const int4* rp = reinterpret_cast<const int4*>(rects + (size_t)n * 16);
+    *reinterpret_cast<int4*>(r) = __ldg(rp); *reinterpret_cast<int4*>(r + 8) = __ldg(rp + 1);
+    if (rect_hit(r, h, w)) return;
+  }
+  const float* t = xf + (size_t)n * 8;
+  const AffTap a = affine_taps(t, h, w, H, W);
+  const T* q = dz + ((size_t)blockIdx.y * HW + px) * CP;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* pl = adv + ((size_t)b * 3 + c) * HW;
+    const float v = a.w00 * pl[a.i00] + a.w01 * pl[a.i01] + a.w10 * pl[a.i10] + a.w11 * pl[a.i11];
+    const float vc = t[6] * (v - 0.5f) + 0.5f + t[7];
+    if (vc < 0.f || vc > 1.f) continue;                 // torch.clamp passes the gradient on [min, max]
+    const float g = 2.f * t[6] * to_float(q[c]);
+    float* gp = G + ((size_t)b * 3 + c) * HW;
+    if (a.w00 != 0.f) atomicAdd(gp + a.i00, a.w00 * g);
+    if (a.w01 != 0.f) atomicAdd(gp + a.i01, a.w01 * g);
+    if (a.w10 != 0.f) atomicAdd(gp + a.i10, a.w10 * g);
+    if (a.w11 != 0.f) atomicAdd(gp + a.i11, a.w11 * g);
+  }
+}
+
+void launch_expand_affine(const float* adv, const float* xf, const int16_t* rects, void* out, int S, int n0, int n,
+                          int H, int W, int Cp, bool bf16, cudaStream_t st) {
+  dim3 grid((H * W + 255) / 256, n);
+#define EA(TT, CPV) expand_affine_kernel<TT, CPV><<<grid, 256, 0, st>>>(adv, xf, rects, (TT*)out, S, n0, H, W)
+  if (bf16) { if (Cp == 3) EA(__nv_bfloat16, 3); else if (Cp == 4) EA(__nv_bfloat16, 4); else EA(__nv_bfloat16, 8); }
+  else { if (Cp == 3) EA(float, 3); else if (Cp == 4) EA(float, 4); else EA(float, 8); }
+#undef EA
+}
+void launch_reduce_affine(const void* dz, const float* adv, const float* xf, const int16_t* rects, float* G, int S, int n0,
+                          int n, int H, int W, int Cp, bool bf16, cudaStream_t st) {
+  dim3 grid((H * W + 255) / 256, n);
+#define RA(TT, CPV) reduce_affine_kernel<TT, CPV><<<grid, 256, 0, st>>>((const TT*)dz, adv, xf, rects, G, S, n0, H, W)
+  if (bf16) { if (Cp == 4) RA(__nv_bfloat16, 4); else if (Cp == 3) RA(__nv_bfloat16, 3); else RA(__nv_bfloat16, 8); }
+  else { if (Cp == 4) RA(float, 4); else if (Cp == 3) RA(float, 3); else RA(float, 8); }
+#undef RA
+}
+
+// =====================================================================================
 // K4: CW loss / argmax / dlogits -- one warp per sample
 // =====================================================================================
 __global__ void cw_kernel(const float* __restrict__ logits, const int32_t* __restrict__ y,

@@ -156,7 +156,7 @@ class Engine:
 
     # ------------------------------------------------------------------------------
     def attack_grad(self, x, mask, pattern, rects, y, crit_targeted, confidence, eps, stage, grad_adv,
-                    S_total=None, host=False):
+                    S_total=None, host=False, xforms=None):
         """attack.py:184-247.  rects [B,S,4,4] int16; y [B]; crit_targeted [B] bool.
         Fills grad_adv [B,3,H,W] and returns a dict of host numpy results."""
         B = x.shape[0]
@@ -186,7 +186,11 @@ class Engine:
         a.loss_density_host = res["loss_density"].ctypes.data
         a.group_lasso_host = res["group_lasso"].ctypes.data
         a.l2_host = res["l2"].ctypes.data
-        self._live = (rects, yh, th, res)
+        xf = None
+        if xforms is not None:        # optional affine / colour EOT: [B,S,8] float32
+            xf = np.ascontiguousarray(xforms, dtype=np.float32).reshape(N, 8)
+            a.xform_host = xf.ctypes.data
+        self._live = (rects, yh, th, res, xf)
         if host:
             return a, res
         _lib.check(self.lib.dp_attack_grad(self.handle, C.byref(a), self._stream()))

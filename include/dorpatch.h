@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DP_ABI_VERSION 2
+#define DP_ABI_VERSION 3
 
 enum dp_precision {
   DP_PREC_FP32 = 0, /* fp32 storage, fp32 FMA math (no tensor cores): parity checks   */
@@ -132,6 +132,10 @@ typedef struct dp_attack_args {
   float* loss_density_host;  /* [B] (stage 0; else untouched)                        */
   float* group_lasso_host;   /* [B] (stage 0; else untouched)                        */
   float* l2_host;            /* [B] ||delta||_2 before clipping                      */
+  /* optional affine / colour EOT (not in the reference, NULL = off = reference
+   * behaviour): [B*S][8] = {t00,t01,t02,t10,t11,t12 (affine_grid theta, align_corners=False,
+   * border padding), contrast, brightness}; applied to adv_x before the occlusion. */
+  const float* xform_host;
 } dp_attack_args;
 
 /* attack.py:184-247 up to (and including) backward; leaves per-image state

@@ -136,7 +136,7 @@ def set_target(preds_adv, label):
 # ----------------------------------------------------------------------------
 def step_losses_and_grads(model, x, mask, pattern, y, idx, universe, crit_targeted, n_classes,
                           confidence, structured, density, coeff_group_lasso, stage, eps,
-                          local_var_x, idx_dual=None, basic_unit=7):
+                          local_var_x, idx_dual=None, basic_unit=7, xforms=None):
     """x,pattern [B,3,H,W]; mask [B,1,H,W]; y [B] int64; idx [B,S] int (per-image
     mask indices); crit_targeted [B] bool; structured / coeff_group_lasso [B]
     python floats; returns a dict of tensors (all detached)."""
@@ -147,7 +147,11 @@ def step_losses_and_grads(model, x, mask, pattern, y, idx, universe, crit_target
     delta = clip_paste(mask, pattern, x, eps)
     adv_x = x + delta
     keep = universe[torch.as_tensor(np.asarray(idx).reshape(-1))].reshape(B, S, 1, H, W)
-    xm = occlude(adv_x[:, None], keep)
+    src = adv_x[:, None]
+    if xforms is not None:                       # optional affine / colour EOT (not in the reference)
+        from . import eot as _eot
+        src = _eot.apply(adv_x, xforms)
+    xm = occlude(src, keep)
     if idx_dual is not None:
         keep2 = universe[torch.as_tensor(np.asarray(idx_dual).reshape(-1))].reshape(B, S, 1, H, W)
         xm = occlude(xm, keep2)

@@ -228,3 +228,32 @@ def test_window_sum(engine_factory):
     got = e.window_sum(m.to(DEV), 7)
     ref = OA.window_sum(m, 7).reshape(2, -1).numpy()
     assert np.allclose(got, ref, rtol=1e-5)
+
+
+def test_affine_colour_eot_step_matches_torch_oracle(engine_factory, oracle_net):
+    """Optional affine / colour EOT (not in the reference; oracle = F.affine_grid/grid_sample):
+    one step with per-sample transforms, fp32 engine.  loss 2e-3 abs; grad cosine >= 0.999."""
+    from dorpatch_b200 import eot as PE
+    H, B, S = 112, 2, 3
+    e = engine_factory(img=H, precision="fp32", chunk=4, max_images=4)
+    x, m, p = _rand((B, 3, H, H), 51), _rand((B, 1, H, H), 52), _rand((B, 3, H, H), 53)
+    y = torch.tensor([17, 400])
+    targeted = [True, False]
+    idx = np.random.RandomState(4).randint(0, 2520, (B, S))
+    rects = _rects_for(H, idx, 2)
+    xf = PE.sample(np.random.RandomState(9), B, S, affine=1.0, colour=1.0)
+    xf[0, 0] = [1, 0, 0, 0, 1, 0, 1, 0]                              # identity transform on one sample
+    G = torch.zeros(B, 3, H, H, device=DEV)
+    xd, md, pd = x.to(DEV), m.to(DEV).clone(), p.to(DEV).clone()
+    r = e.attack_grad(xd, md, pd, rects, y.numpy(), targeted, 0.1, 4.0, 1, G, xforms=xf)
+    gp = torch.zeros_like(pd)
+    e.attack_update(xd, md, pd, G, np.zeros(B, np.float32), [0.0, 0.0], None, 0.0, 1, grad_pattern_out=gp)
+    torch.cuda.synchronize()
+    uni = torch.from_numpy(OM.rects_to_bool(OM.universe_rects(H, 2), H))
+    o = OA.step_losses_and_grads(oracle_net, x, m, p, y, idx, uni, targeted, 1000, 0.1, [0.0, 0.0], 0.0, [0.0, 0.0], 1,
+                                 4.0, OA.local_variance(x)[0].mean(1), xforms=xf)
+    print("eot loss", r["loss_adv"], o["loss_adv"].numpy())
+    assert np.abs(r["loss_adv"] - o["loss_adv"].numpy()).max() <= 2e-3
+    cos = _cos(gp.cpu(), o["grad_pattern"])
+    print("eot grad cos", cos)
+    assert cos >= 0.999, cos
