@@ -522,14 +522,16 @@ __global__ void __launch_bounds__(gnc::THREADS) gn_fwd_cluster_kernel(const T* _
       if (nbuf == 2 && n + n_clusters < N)
         pipe.issue(slabs + (size_t)(b ^ 1) * slab_stride, x + ((size_t)(n + n_clusters) * P + p0) * C, slab_bytes, b ^ 1);
     }
-    const T* slab = reinterpret_cast<const T*>(slabs + (size_t)b * slab_stride);
+    const uint32_t slab_a = gnc::smem_u32(slabs + (size_t)b * slab_stride) + (uint32_t)((trow * C + tcol * V) * sizeof(T));
+    const uint32_t srow = (uint32_t)(rpi * C * sizeof(T));
     pipe.wait(b, parity);
 
     float a[V], bq[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) { a[i] = 0.f; bq[i] = 0.f; }
-    for (int r = trow; r < rows; r += rpi) {
-      Vec<T> v; v.load(slab + (size_t)r * C + tcol * V);
+    uint32_t sp = slab_a;
+    for (int r = trow; r < rows; r += rpi, sp += srow) {
+      Vec<T> v; v.load_shared(sp);
       float f[V]; v.unpack(f);
 #pragma unroll
       for (int i = 0; i < V; ++i) { a[i] += f[i]; bq[i] = fmaf(f[i], f[i], bq[i]); }
@@ -564,13 +566,15 @@ __global__ void __launch_bounds__(gnc::THREADS) gn_fwd_cluster_kernel(const T* _
       sa[i] = s_rstd[g] * gamma[c];
       sb[i] = beta[c] - s_mean[g] * sa[i];
     }
-    T* dst = y + ((size_t)n * P + p0) * C;
-    for (int r = trow; r < rows; r += rpi) {
-      Vec<T> v; v.load(slab + (size_t)r * C + tcol * V);
+    T* dst = y + ((size_t)n * P + p0) * C + (size_t)trow * C + tcol * V;
+    const size_t grow = (size_t)rpi * C;
+    sp = slab_a;
+    for (int r = trow; r < rows; r += rpi, sp += srow, dst += grow) {
+      Vec<T> v; v.load_shared(sp);
       float f[V]; v.unpack(f);
 #pragma unroll
       for (int i = 0; i < V; ++i) f[i] = fmaxf(fmaf(sa[i], f[i], sb[i]), 0.f);
-      v.pack(f); v.store(dst + (size_t)r * C + tcol * V);
+      v.pack(f); v.store(dst);
     }
     __syncthreads();            // slab b, tp, s_mean free for the next iteration
     cluster.barrier_wait();     // every peer has read our partials: `part` may be rewritten / we may exit
@@ -619,7 +623,8 @@ __global__ void __launch_bounds__(gnc::THREADS, 2) gn_bwd_cluster_kernel(const T
       if (nbuf == 2 && n + n_clusters < N)
         pipe.issue(slabs + (size_t)(b ^ 1) * slab_stride, x + ((size_t)(n + n_clusters) * P + p0) * C, slab_bytes, b ^ 1);
     }
-    const T* slab = reinterpret_cast<const T*>(slabs + (size_t)b * slab_stride);
+    const uint32_t slab_a = gnc::smem_u32(slabs + (size_t)b * slab_stride) + (uint32_t)(tcol * V * sizeof(T));
+    const uint32_t crow = (uint32_t)(C * sizeof(T));
     float sa[V], sb[V], mu[GV], rs[GV];
 #pragma unroll
     for (int i = 0; i < GV; ++i) {
@@ -647,7 +652,7 @@ __global__ void __launch_bounds__(gnc::THREADS, 2) gn_bwd_cluster_kernel(const T
       for (int u = 0; u < U; ++u) {
         const int r = r0 + u * rpi;
         if (r < rows) {
-          Vec<T> vx; vx.load(slab + (size_t)r * C + tcol * V);
+          Vec<T> vx; vx.load_shared(slab_a + (uint32_t)r * crow);
           float fx[V], fd[V]; vx.unpack(fx); vd[u].unpack(fd);
 #pragma unroll
           for (int i = 0; i < V; ++i) {
@@ -693,7 +698,7 @@ __global__ void __launch_bounds__(gnc::THREADS, 2) gn_bwd_cluster_kernel(const T
         const int r = r0 + u * rpi;
         if (r < rows) {
           const size_t off = base + (size_t)r * C + tcol * V;
-          Vec<T> vx; vx.load(slab + (size_t)r * C + tcol * V);
+          Vec<T> vx; vx.load_shared(slab_a + (uint32_t)r * crow);
           float fx[V], fd[V], fo[V]; vx.unpack(fx); vd[u].unpack(fd);
           if (addend != nullptr) va[u].unpack(fo);
           else {
