@@ -213,39 +213,53 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
         if (lane == 0) { ptx::bulk_store(dst, clean_b, out_bytes); ptx::bulk_commit(); }
         continue;
       }
+      // per-sample, row-independent classification of this lane's chunks (ch = lane + 32*j) against
+      // each rectangle's element interval: bit j of in_k = chunk fully inside, of pa_k = straddles an edge
+      uint32_t in_k[4], pa_k[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t bi = 0u, bp = 0u;
+        for (int j = 0, ch = lane; ch < row_chunks; ++j, ch += 32) {
+          const int e0 = ch * EPC;
+          const bool inside = e0 >= el[k] && e0 + EPC <= eh[k];
+          const bool part = !inside && e0 < eh[k] && e0 + EPC > el[k];
+          bi |= (inside ? 1u : 0u) << j;
+          bp |= (part ? 1u : 0u) << j;
+        }
+        in_k[k] = bi; pa_k[k] = bp;
+      }
 #pragma unroll
       for (int rr = 0; rr < EXP_R; ++rr) {
         const int row = r0 + rr;
-        bool cov[4], rany = false;
+        uint32_t zero_bits = 0u, part_bits = 0u;
+        bool rany = false;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { cov[k] = row >= rr0[k] && row < rr1[k]; rany = rany || cov[k]; }
+        for (int k = 0; k < 4; ++k) {
+          const bool cov = row >= rr0[k] && row < rr1[k];
+          rany = rany || cov;
+          zero_bits |= cov ? in_k[k] : 0u;
+          part_bits |= cov ? pa_k[k] : 0u;
+        }
         if (!rany) {                                            // clean row: bulk store
           if (lane == 0) { ptx::bulk_store(dst + (size_t)rr * row_bytes, clean_b + (size_t)rr * row_bytes, row_bytes); ptx::bulk_commit(); }
           continue;
         }
+        part_bits &= ~zero_bits;
         const uint4* crow = reinterpret_cast<const uint4*>(clean_b + (size_t)rr * row_bytes);
         uint4* drow = reinterpret_cast<uint4*>(dst + (size_t)rr * row_bytes);
-        for (int ch = lane; ch < row_chunks; ch += 32) {
-          const int e0 = ch * EPC;
-          bool zero = false, partial = false;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (cov[k]) {
-              if (e0 >= el[k] && e0 + EPC <= eh[k]) zero = true;
-              else if (e0 < eh[k] && e0 + EPC > el[k]) partial = true;
-            }
-          }
+        for (int j = 0, ch = lane; ch < row_chunks; ++j, ch += 32) {
           uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (!zero) {
+          if (!((zero_bits >> j) & 1u)) {
             v = crow[ch];
-            if (partial) {
+            if ((part_bits >> j) & 1u) {                        // <= 2 chunks per rectangle edge
               T* ev = reinterpret_cast<T*>(&v);
+              const int e0 = ch * EPC;
 #pragma unroll
-              for (int j = 0; j < EPC; ++j) {
+              for (int q = 0; q < EPC; ++q) {
                 bool z = false;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) z = z || (cov[k] && e0 + j >= el[k] && e0 + j < eh[k]);
-                if (z) ev[j] = from_float<T>(0.f);
+                for (int k = 0; k < 4; ++k) z = z || (row >= rr0[k] && row < rr1[k] && e0 + q >= el[k] && e0 + q < eh[k]);
+                if (z) ev[q] = from_float<T>(0.f);
               }
             }
           }
