@@ -721,27 +721,41 @@ __global__ void __launch_bounds__(gnc::THREADS, 2) gn_bwd_cluster_kernel(const T
   }
 }
 
-struct GnPlan { int cl; int nbuf; size_t smem; uint32_t slab_stride; int ctas_per_sm; };
+struct GnPlan { int cl; int nbuf; size_t smem; uint32_t slab_stride; int ctas_per_sm; bool persistent; };
+// Tunables (environment, read once): DORPATCH_GN=twopass disables the cluster kernels;
+// DORPATCH_GN_PERSIST=1 -> persistent clusters with double-buffered slab prefetch (measured slower on
+// B200 than one cluster per sample: fewer resident CTAs); DORPATCH_GN_SOFT=<KB> per-CTA smem budget
+// used to pick the cluster size.
 static bool gn_plan(int P, int C, size_t es, GnPlan* out) {
-  static int mode = -1;
-  if (mode < 0) { const char* e = getenv("DORPATCH_GN"); mode = (e && strcmp(e, "twopass") == 0) ? 0 : 1; }
+  static int mode = -1, persist = 0;
+  static size_t soft = 111 * 1024;
+  if (mode < 0) {
+    const char* e = getenv("DORPATCH_GN"); mode = (e && strcmp(e, "twopass") == 0) ? 0 : 1;
+    if (const char* p = getenv("DORPATCH_GN_PERSIST")) persist = atoi(p);
+    if (const char* q = getenv("DORPATCH_GN_SOFT")) soft = (size_t)atoi(q) * 1024;
+  }
   if (!mode) return false;
   if (C / (int)(16 / es) > gnc::THREADS) return false;
-  const size_t fixed = gnc::HDR + gnc::TP_BYTES;
-  const size_t budget2 = 111 * 1024, budget1 = 220 * 1024;   // smem per CTA for two / one CTA per SM
+  const size_t fixed = gnc::HDR + gnc::TP_BYTES, hard = 220 * 1024;
   for (int cl = 1; cl <= 8; cl *= 2) {
     if (cl > P) break;
     const size_t slab = (((size_t)((P + cl - 1) / cl)) * C * es + 127) / 128 * 128;
-    if (fixed + 2 * slab <= budget2) { *out = GnPlan{cl, 2, fixed + 2 * slab, (uint32_t)slab, 2}; return true; }
-    if (cl == 8) {
-      if (fixed + 2 * slab <= budget1) { *out = GnPlan{cl, 2, fixed + 2 * slab, (uint32_t)slab, 1}; return true; }
-      if (fixed + slab <= budget1) { *out = GnPlan{cl, 1, fixed + slab, (uint32_t)slab, 1}; return true; }
+    if (persist) {
+      if (fixed + 2 * slab <= soft) { *out = GnPlan{cl, 2, fixed + 2 * slab, (uint32_t)slab, (int)(hard / (fixed + 2 * slab)), true}; return true; }
+      if (cl == 8) {
+        if (fixed + 2 * slab <= hard) { *out = GnPlan{cl, 2, fixed + 2 * slab, (uint32_t)slab, 1, true}; return true; }
+        if (fixed + slab <= hard) { *out = GnPlan{cl, 1, fixed + slab, (uint32_t)slab, 1, true}; return true; }
+      }
+    } else if (fixed + slab <= soft || (cl == 8 && fixed + slab <= hard)) {
+      *out = GnPlan{cl, 1, fixed + slab, (uint32_t)slab, 1, false};
+      return true;
     }
   }
   return false;
 }
 static int g_num_sms = 0;
 static int gn_grid(const GnPlan& pl, int N) {
+  if (!pl.persistent) return pl.cl * N;                       // one cluster per sample
   if (g_num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
   int n_clusters = (g_num_sms * pl.ctas_per_sm) / pl.cl;
   if (n_clusters < 1) n_clusters = 1;
