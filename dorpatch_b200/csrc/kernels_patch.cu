@@ -104,6 +104,8 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 constexpr int EXP_R = 4;          // image rows per tile
 constexpr int EXP_THREADS = 256;
 constexpr int EXP_WARPS = EXP_THREADS / 32;
+constexpr int EXP_HDR = 512 + 4096;   // mbarrier + per-item rectangle cache (128 samples x 32 B)
+constexpr int EXP_RCACHE = 128;
 
 __device__ __forceinline__ bool rect_hit(const short* r, int row, int col) {
 #pragma unroll
@@ -136,8 +138,9 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
   const uint32_t out_bytes = row_bytes * EXP_R;
   const int row_chunks = row_elems / EPC;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-  float* in = reinterpret_cast<float*>(smem + 512);
-  unsigned char* clean_b = smem + 512 + NP * plane_bytes;
+  int4* srect = reinterpret_cast<int4*>(smem + 512);
+  float* in = reinterpret_cast<float*>(smem + EXP_HDR);
+  unsigned char* clean_b = smem + EXP_HDR + NP * plane_bytes;
   T* clean = reinterpret_cast<T*>(clean_b);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -171,6 +174,11 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
         for (int c = 0; c < 3; ++c) ptx::bulk_load(in + c * tile_px, p.img + ((size_t)(b * 3 + c) * H + r0) * W, plane_bytes, bar);
       }
     }
+    // rectangle cache of this item's samples (hides the per-sample global-load latency)
+    const bool cached = p.rects != nullptr && (s_hi - s_lo) <= EXP_RCACHE;
+    if (cached)
+      for (int i = threadIdx.x; i < 2 * (s_hi - s_lo); i += EXP_THREADS)
+        srect[i] = __ldg(reinterpret_cast<const int4*>(p.rects + (size_t)s_lo * 16) + i);
     ptx::mbar_wait(bar, phase);
     phase ^= 1u;
 
@@ -198,8 +206,12 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
       int rr0[4], rr1[4], el[4], eh[4];
       bool any = false;
       if (p.rects != nullptr) {
-        const int4* rp = reinterpret_cast<const int4*>(p.rects + (size_t)n * 16);
-        const int4 q0 = __ldg(rp), q1 = __ldg(rp + 1);       // same address in every lane: broadcast
+        int4 q0, q1;
+        if (cached) { q0 = srect[2 * (n - s_lo)]; q1 = srect[2 * (n - s_lo) + 1]; }
+        else {
+          const int4* rp = reinterpret_cast<const int4*>(p.rects + (size_t)n * 16);
+          q0 = __ldg(rp); q1 = __ldg(rp + 1);                 // same address in every lane: broadcast
+        }
         const int w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -275,7 +287,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
 
 template <typename T, int CP, bool FUSED>
 static void expand_launch(const ExpandParams& p, int num_sms, cudaStream_t st) {
-  const size_t smem = 512 + (size_t)(FUSED ? 7 : 3) * EXP_R * p.W * 4 + (size_t)EXP_R * p.W * CP * sizeof(T);
+  const size_t smem = EXP_HDR + (size_t)(FUSED ? 7 : 3) * EXP_R * p.W * 4 + (size_t)EXP_R * p.W * CP * sizeof(T);
   cudaFuncSetAttribute(expand_kernel<T, CP, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ExpandParams q = p;
   const int nb = (p.n0 + p.n - 1) / p.S - p.n0 / p.S + 1;
