@@ -257,3 +257,38 @@ def test_affine_colour_eot_step_matches_torch_oracle(engine_factory, oracle_net)
     cos = _cos(gp.cpu(), o["grad_pattern"])
     print("eot grad cos", cos)
     assert cos >= 0.999, cos
+
+
+def test_reference_named_helpers_on_gpu(oracle_params):
+    """utils.clip / DorPatch.patch_selection / DorPatch.collect_failure keep the reference's signatures
+    and semantics (utils.py:105-110, attack.py:363-406) on the native engine."""
+    import os
+    from dorpatch_b200 import masks as PM
+    from dorpatch_b200.attack import DorPatch
+    from dorpatch_b200.resnetv2 import ResNetV2
+    from dorpatch_b200.utils import NormModel, clip, get_normalize
+    os.environ["DORPATCH_PRECISION"] = "fp32"
+    os.environ["DORPATCH_CHUNK"] = "16"
+    H = 112
+    x, m, p = _rand((2, 3, H, H), 61), _rand((2, 1, H, H), 62), _rand((2, 3, H, H), 63)
+    d = clip(m.to(DEV), p.to(DEV), x.to(DEV), 4.0)
+    assert (d.cpu() - OA.clip_paste(m, p, x, 4.0)).abs().max().item() <= 1e-6
+    sel = DorPatch().patch_selection(m.to(DEV), 0.10)
+    assert torch.equal(sel.cpu(), OA.patch_selection(m, 0.10))
+    net = ResNetV2(seed=0)
+    net.load_state_dict(oracle_params)
+    model = torch.nn.DataParallel(NormModel(net, get_normalize("imagenet", "resnetv2"))).cuda().eval()
+    onet = OR.OracleNet(oracle_params, weights_require_grad=False).eval()
+    uni = torch.from_numpy(OM.rects_to_bool(OM.universe_rects(H, 1), H))
+    with torch.no_grad():
+        logits = onet(OA.occlude(x[:1], uni))
+    y = int(logits.argmax(1).mode()[0])
+    ref_failed = OA.collect_failure(onet, x[:1], y, uni, False, 64)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        got = DorPatch().collect_failure(x[:1].to(DEV), torch.tensor([y]), PM.universe(H, 1), False, model, batch_size=64)
+        got_bool = DorPatch().collect_failure(x[:1].to(DEV), torch.tensor([y] * 64).to(DEV), uni.to(DEV), False, model, batch_size=64)
+    top2 = logits.topk(2, dim=1).values
+    unsure = set(np.nonzero(((top2[:, 0] - top2[:, 1]) < 1e-3).numpy())[0].tolist())
+    assert set(got) ^ set(ref_failed) <= unsure
+    assert set(got_bool) ^ set(ref_failed) <= unsure
