@@ -721,6 +721,114 @@ __global__ void __launch_bounds__(gnc::THREADS, 2) gn_bwd_cluster_kernel(const T
   }
 }
 
+// Backward variant with BOTH x and dy slabs resident in shared memory (two TMA loads issued up front,
+// no global-load latency chains in either pass).  One cluster per sample; used when two slabs fit the
+// per-CTA budget.
+template <typename T, bool UG>
+__global__ void __launch_bounds__(gnc::THREADS, 2) gn_bwd_cluster_smem_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                               const T* __restrict__ addend, T* __restrict__ dx,
+                                                                               const float* __restrict__ gamma,
+                                                                               const float* __restrict__ beta,
+                                                                               const float* __restrict__ stats, int P, int C,
+                                                                               uint32_t slab_stride) {
+  constexpr int V = Vec<T>::N;
+  constexpr int GV = UG ? 1 : V;
+  extern __shared__ __align__(128) unsigned char smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int n = blockIdx.x / CL;
+  gnc::Pipe pipe{reinterpret_cast<uint64_t*>(smem), 2};
+  float* part = reinterpret_cast<float*>(smem + 64);
+  float* s_1 = reinterpret_cast<float*>(smem + 64 + 256);
+  float* s_2 = s_1 + GN_GROUPS;
+  float* tp = reinterpret_cast<float*>(smem + gnc::HDR);
+  unsigned char* slabs = smem + gnc::HDR + gnc::TP_BYTES;
+
+  const int p0 = (int)(((long long)P * rank) / CL), p1 = (int)(((long long)P * (rank + 1)) / CL);
+  const int rows = p1 - p0;
+  const uint32_t slab_bytes = (uint32_t)((size_t)rows * C * sizeof(T));
+  const size_t base = ((size_t)n * P + p0) * C;
+  const int cols = C / V, rpi = gnc::THREADS / cols, cpg = C / GN_GROUPS;
+  const int tcol = threadIdx.x % cols, trow = threadIdx.x / cols;
+  pipe.init();
+  if (threadIdx.x == 0) {
+    pipe.issue(slabs, x + base, slab_bytes, 0);
+    pipe.issue(slabs + slab_stride, dy + base, slab_bytes, 1);
+  }
+  float ga[V], sa[V], sb[V], mu[GV], rs[GV];
+#pragma unroll
+  for (int i = 0; i < GV; ++i) {
+    const int g = (tcol * V + i) / cpg;
+    mu[i] = stats[((size_t)n * GN_GROUPS + g) * 2 + 0];
+    rs[i] = stats[((size_t)n * GN_GROUPS + g) * 2 + 1];
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    ga[i] = gamma[tcol * V + i];
+    sa[i] = rs[UG ? 0 : i] * ga[i];
+    sb[i] = beta[tcol * V + i] - mu[UG ? 0 : i] * sa[i];
+  }
+  const uint32_t xa = gnc::smem_u32(slabs) + (uint32_t)((trow * C + tcol * V) * sizeof(T));
+  const uint32_t da = xa + slab_stride;
+  const uint32_t srow = (uint32_t)(rpi * C * sizeof(T));
+  pipe.wait(0, 0);
+  pipe.wait(1, 0);
+  float a[V], bq[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { a[i] = 0.f; bq[i] = 0.f; }
+  uint32_t off = 0;
+  for (int r = trow; r < rows; r += rpi, off += srow) {
+    Vec<T> vx, vd; vx.load_shared(xa + off); vd.load_shared(da + off);
+    float fx[V], fd[V]; vx.unpack(fx); vd.unpack(fd);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float pre = fmaf(sa[i], fx[i], sb[i]);
+      const float dg = pre > 0.f ? fd[i] * ga[i] : 0.f;
+      const float xh = (fx[i] - mu[UG ? 0 : i]) * rs[UG ? 0 : i];
+      a[i] += dg; bq[i] = fmaf(dg, xh, bq[i]);
+    }
+  }
+  gnc::cta_group_reduce<V>(a, bq, C, tp, part);
+  cluster.sync();
+  if (threadIdx.x < GN_GROUPS) {
+    float s = 0.f, q = 0.f;
+    for (int r = 0; r < CL; ++r) {
+      const float* rp = cluster.map_shared_rank(part, r);
+      s += rp[threadIdx.x * 2 + 0];
+      q += rp[threadIdx.x * 2 + 1];
+    }
+    const float inv_m = 1.0f / ((float)P * cpg);
+    s_1[threadIdx.x] = s * inv_m;
+    s_2[threadIdx.x] = q * inv_m;
+  }
+  __syncthreads();
+  cluster.barrier_arrive();
+  float m1[GV], m2[GV];
+#pragma unroll
+  for (int i = 0; i < GV; ++i) { const int g = (tcol * V + i) / cpg; m1[i] = s_1[g]; m2[i] = s_2[g]; }
+  const size_t grow = (size_t)rpi * C;
+  size_t goff = base + (size_t)trow * C + tcol * V;
+  off = 0;
+  for (int r = trow; r < rows; r += rpi, off += srow, goff += grow) {
+    Vec<T> vx, vd; vx.load_shared(xa + off); vd.load_shared(da + off);
+    float fx[V], fd[V], fo[V]; vx.unpack(fx); vd.unpack(fd);
+    if (addend != nullptr) { Vec<T> va; va.load(addend + goff); va.unpack(fo); }
+    else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) fo[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float pre = fmaf(sa[i], fx[i], sb[i]);
+      const float dg = pre > 0.f ? fd[i] * ga[i] : 0.f;
+      const float xh = (fx[i] - mu[UG ? 0 : i]) * rs[UG ? 0 : i];
+      fo[i] += rs[UG ? 0 : i] * (dg - m1[UG ? 0 : i] - xh * m2[UG ? 0 : i]);
+    }
+    Vec<T> vo; vo.pack(fo); vo.store(dx + goff);
+  }
+  cluster.barrier_wait();
+}
+
 struct GnPlan { int cl; int nbuf; size_t smem; uint32_t slab_stride; int ctas_per_sm; bool persistent; };
 // Tunables (environment, read once): DORPATCH_GN=twopass disables the cluster kernels;
 // DORPATCH_GN_PERSIST=1 -> persistent clusters with double-buffered slab prefetch (measured slower on
@@ -1029,10 +1137,31 @@ void launch_gn_relu_backward(const void* dy, const void* x, const void* addend, 
                              const float* beta, const float* stats, float* partial, int N, int P, int C, bool bf16,
                              cudaStream_t st) {
   GnPlan pl;
+  const bool ug = (C / GN_GROUPS) >= (bf16 ? 8 : 4);
+  {   // both slabs in shared memory when they fit (DORPATCH_GN_DYSMEM=0 disables)
+    static int dys = -1;
+    if (dys < 0) { const char* e = getenv("DORPATCH_GN_DYSMEM"); dys = e ? atoi(e) : 1; }
+    const size_t es = bf16 ? 2 : 4, fixed = gnc::HDR + gnc::TP_BYTES;
+    if (dys && gn_plan(P, C, es, &pl) && !pl.persistent && C / (int)(16 / es) <= gnc::THREADS) {
+      for (int cl = 1; cl <= 8; cl *= 2) {
+        if (cl > P) break;
+        const size_t slab = (((size_t)((P + cl - 1) / cl)) * C * es + 127) / 128 * 128;
+        if (fixed + 2 * slab <= 111 * 1024) {
+          bool ok;
+#define GNS(TT, UGV) launch_cluster(gn_bwd_cluster_smem_kernel<TT, UGV>, cl, cl * N, fixed + 2 * slab, st, (const TT*)dy, (const TT*)x, (const TT*)addend, (TT*)dx, gamma, beta, stats, P, C, (uint32_t)slab)
+          if (bf16) ok = ug ? GNS(__nv_bfloat16, true) : GNS(__nv_bfloat16, false);
+          else ok = ug ? GNS(float, true) : GNS(float, false);
+#undef GNS
+          if (ok) return;
+          cudaGetLastError();
+          break;
+        }
+      }
+    }
+  }
   if (gn_plan(P, C, bf16 ? 2 : 4, &pl)) {
     const int grid = gn_grid(pl, N);
     bool ok;
-    const bool ug = (C / GN_GROUPS) >= (bf16 ? 8 : 4);
 #define GNB(TT, UGV) launch_cluster(gn_bwd_cluster_kernel<TT, UGV>, pl.cl, grid, pl.smem, st, (const TT*)dy, (const TT*)x, (const TT*)addend, (TT*)dx, gamma, beta, stats, N, P, C, pl.nbuf, pl.slab_stride)
     if (bf16) ok = ug ? GNB(__nv_bfloat16, true) : GNB(__nv_bfloat16, false);
     else ok = ug ? GNB(float, true) : GNB(float, false);
