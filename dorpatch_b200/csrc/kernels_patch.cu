@@ -9,6 +9,8 @@
 //   maskreg  attack.py:72-80,235-245                        density + group-lasso values / statistics
 //   update   K3: attack.py:332-342                          chain rule through clip + sign step + clip
 // (file:line into /root/reference).  Images are NCHW fp32; network input is NHWC(Cp) T.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -101,7 +103,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 }  // namespace ptx
 
-constexpr int EXP_R = 4;          // image rows per tile
+constexpr int EXP_R_DEFAULT = 4;  // image rows per tile (DORPATCH_K1_ROWS overrides; must divide H)
 constexpr int EXP_THREADS = 256;
 constexpr int EXP_WARPS = EXP_THREADS / 32;
 constexpr int EXP_HDR = 512 + 4096;   // mbarrier + per-item rectangle cache (128 samples x 32 B)
@@ -117,7 +119,7 @@ __device__ __forceinline__ bool rect_hit(const short* r, int row, int col) {
 struct ExpandParams {
   const float* img; const float* x; const float* mask; const float* pattern; const float* scale;
   const int16_t* rects; void* out;
-  int B, S, n0, n, H, W, sgroups;
+  int B, S, n0, n, H, W, sgroups, R;
 };
 
 // Shared memory (dynamic): [mbarrier, 512 B][input planes NP*R*W fp32][clean tile R*W*CP T].
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
   constexpr int EPC = 16 / (int)sizeof(T);                 // elements per 16-byte chunk
   extern __shared__ __align__(128) unsigned char smem[];
   const int W = p.W, H = p.H, HW = H * W;
+  const int EXP_R = p.R;
   const int tile_px = EXP_R * W;
   const uint32_t plane_bytes = (uint32_t)tile_px * 4u;
   const int row_elems = W * CP;
@@ -240,7 +243,6 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
         }
         in_k[k] = bi; pa_k[k] = bp;
       }
-#pragma unroll
       for (int rr = 0; rr < EXP_R; ++rr) {
         const int row = r0 + rr;
         uint32_t zero_bits = 0u, part_bits = 0u;
@@ -287,9 +289,14 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
 
 template <typename T, int CP, bool FUSED>
 static void expand_launch(const ExpandParams& p, int num_sms, cudaStream_t st) {
+  static int rows_env = -1;
+  if (rows_env < 0) { const char* e = getenv("DORPATCH_K1_ROWS"); rows_env = e ? atoi(e) : EXP_R_DEFAULT; if (rows_env < 1) rows_env = EXP_R_DEFAULT; }
+  int EXP_R = rows_env;
+  while (EXP_R > 1 && (p.H % EXP_R != 0 || (size_t)EXP_R * p.W * ((FUSED ? 7 : 3) * 4 + CP * sizeof(T)) > 200 * 1024)) EXP_R /= 2;
   const size_t smem = EXP_HDR + (size_t)(FUSED ? 7 : 3) * EXP_R * p.W * 4 + (size_t)EXP_R * p.W * CP * sizeof(T);
   cudaFuncSetAttribute(expand_kernel<T, CP, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ExpandParams q = p;
+  q.R = EXP_R;
   const int nb = (p.n0 + p.n - 1) / p.S - p.n0 / p.S + 1;
   const int tiles = p.H / EXP_R;
   int ctas_per_sm = (int)((200 * 1024) / smem);
@@ -307,7 +314,7 @@ static void expand_launch(const ExpandParams& p, int num_sms, cudaStream_t st) {
 void launch_expand(const float* img, const float* x, const float* mask, const float* pattern, const float* scale,
                    const int16_t* rects, void* out, int B, int S, int n0, int n, int H, int W, int Cp, bool bf16,
                    bool fused, int num_sms, cudaStream_t st) {
-  ExpandParams p{img, x, mask, pattern, scale, rects, out, B, S, n0, n, H, W, 1};
+  ExpandParams p{img, x, mask, pattern, scale, rects, out, B, S, n0, n, H, W, 1, EXP_R_DEFAULT};
 #define EXP_CASE(TT, CPV)                                                   \
   if (fused) expand_launch<TT, CPV, true>(p, num_sms, st);                 \
   else expand_launch<TT, CPV, false>(p, num_sms, st)
