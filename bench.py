@@ -329,6 +329,14 @@ def run_native(args):
             torch.cuda.synchronize()
             tk0.append(e0.elapsed_time(e1))
         k1_ms_clean = float(np.median(tk0))
+        tw = []                                                # context: write-only ceiling (cudaMemset of the same buffer)
+        for _ in range(8):
+            e0.record()
+            buf.zero_()
+            e1.record()
+            torch.cuda.synchronize()
+            tw.append(e0.elapsed_time(e1))
+        write_only_gbs = buf.numel() * buf.element_size() / float(np.median(tw)) / 1e6
         alg_bytes = Nk * IMG * IMG * 3 * es + B * 3 * IMG * IMG * 4
         act_bytes = Nk * IMG * IMG * eng.c_pad * es + B * 3 * IMG * IMG * 4
         traffic = None
@@ -341,7 +349,7 @@ def run_native(args):
                            "achieved": alg_bytes / k1_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
                            "frac": alg_bytes / k1_ms / 1e6 / pk["hbm"], "traffic": traffic,
                            "achieved_incl_channel_pad": act_bytes / k1_ms / 1e6, "ms": k1_ms,
-                           "unoccluded_gbs": alg_bytes / k1_ms_clean / 1e6,
+                           "unoccluded_gbs": alg_bytes / k1_ms_clean / 1e6, "write_only_memset_gbs": write_only_gbs,
                            "algorithmic_bytes_per_launch": alg_bytes, "peak_source": pk["src"]}
         # ---- whole-step tensor roofline + per-category breakdown of one profiled step -------------------
         out["roofline_step"] = {"bound": "tensor", "achieved": GFLOP_PER_SAMPLE * value / world / 1e3, "peak": pk["tf_sus"],

@@ -103,7 +103,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 }  // namespace ptx
 
-constexpr int EXP_R_DEFAULT = 4;  // image rows per tile (DORPATCH_K1_ROWS overrides; must divide H)
+constexpr int EXP_R_DEFAULT = 8;  // image rows per tile (DORPATCH_K1_ROWS overrides; must divide H)
 constexpr int EXP_THREADS = 256;
 constexpr int EXP_WARPS = EXP_THREADS / 32;
 constexpr int EXP_HDR = 512 + 4096;   // mbarrier + per-item rectangle cache (128 samples x 32 B)
