@@ -463,12 +463,21 @@ struct dp_engine {
     auto it = gemm_plans.find(key);
     if (it != gemm_plans.end()) return it->second;
     GemmPlan p;
-    CUBLAS_OK(cublasLtMatmulDescCreate(&p.op, lt_compute, CUDA_R_32F));
-    const cublasOperation_t ta = (mode == 0) ? CUBLAS_OP_T : CUBLAS_OP_N, tb = CUBLAS_OP_N;
+    // modes 2 / 3: the fp32 classifier head (fc forward with fused bias / fc backward), always fp32 math
+    const bool head = mode >= 2;
+    const cudaDataType_t cuda_dt = head ? CUDA_R_32F : this->cuda_dt;
+    CUBLAS_OK(cublasLtMatmulDescCreate(&p.op, head ? CUBLAS_COMPUTE_32F : lt_compute, CUDA_R_32F));
+    const cublasOperation_t ta = (mode == 0 || mode == 2) ? CUBLAS_OP_T : CUBLAS_OP_N, tb = CUBLAS_OP_N;
+    if (mode == 2) {
+      const cublasLtEpilogue_t epi = CUBLASLT_EPILOGUE_BIAS;
+      const void* bias = fc_b;
+      CUBLAS_OK(cublasLtMatmulDescSetAttribute(p.op, CUBLASLT_MATMUL_DESC_EPILOGUE, &epi, sizeof(epi)));
+      CUBLAS_OK(cublasLtMatmulDescSetAttribute(p.op, CUBLASLT_MATMUL_DESC_BIAS_POINTER, &bias, sizeof(bias)));
+    }
     CUBLAS_OK(cublasLtMatmulDescSetAttribute(p.op, CUBLASLT_MATMUL_DESC_TRANSA, &ta, sizeof(ta)));
     CUBLAS_OK(cublasLtMatmulDescSetAttribute(p.op, CUBLASLT_MATMUL_DESC_TRANSB, &tb, sizeof(tb)));
     // column-major view: D[nout x rows] = op(A) * B
-    if (mode == 0) CUBLAS_OK(cublasLtMatrixLayoutCreate(&p.a, cuda_dt, k, nout, k));       // W as col-major [k x nout], ld k
+    if (mode == 0 || mode == 2) CUBLAS_OK(cublasLtMatrixLayoutCreate(&p.a, cuda_dt, k, nout, k));   // W as col-major [k x nout], ld k
     else CUBLAS_OK(cublasLtMatrixLayoutCreate(&p.a, cuda_dt, nout, k, nout));              // W[k rows][nout] as col-major [nout x k], ld nout
     CUBLAS_OK(cublasLtMatrixLayoutCreate(&p.b, cuda_dt, k, rows, k));                      // X / dY as col-major [k x rows]
     CUBLAS_OK(cublasLtMatrixLayoutCreate(&p.c, cuda_dt, nout, rows, nout));
@@ -510,8 +519,8 @@ struct dp_engine {
       cudaEventDestroy(e0); cudaEventDestroy(e1);
       p.tuned = true;
     }
-    const double by = ((double)rows * k + (double)rows * nout * (beta != 0.f ? 2 : 1) + (double)nout * k) * es;
-    PROF(this, mode == 0 ? "gemm1x1_fwd" : "gemm1x1_bwd", by, 2.0 * rows * nout * k, st,
+    const double by = ((double)rows * k + (double)rows * nout * (beta != 0.f ? 2 : 1) + (double)nout * k) * (mode >= 2 ? 4 : es);
+    PROF(this, mode == 0 ? "gemm1x1_fwd" : (mode == 1 ? "gemm1x1_bwd" : (mode == 2 ? "fc_fwd" : "fc_bwd")), by, 2.0 * rows * nout * k, st,
          CUBLAS_OK(cublasLtMatmul(lt, p.op, &one, W, p.a, X, p.b, &beta, Cres ? Cres : D, p.c, D, p.c, &p.algo, lib_ws, lib_ws_bytes, st)));
     ++launches;
   }
@@ -567,8 +576,8 @@ struct dp_engine {
     PROF(this, "head_fwd", (double)N * pl * last.cout * es, 2.0 * N * last.cout * K, st, {
       dp::launch_gn_stats(cur, gn_partial, head_stats, N, pl, last.cout, bf16, st);
       dp::launch_head_pool(cur, head_gn.gamma, head_gn.beta, head_stats, pooled, N, pl, last.cout, bf16, st);
-      dp::launch_fc_forward(pooled, fc_w, fc_b, logits, N, last.cout, K, st);
-    }); KERNEL_OK(); launches += 4;
+    }); KERNEL_OK(); launches += 3;
+    gemm(N, K, last.cout, 2, fc_w, pooled, nullptr, 0.f, logits, st);          // logits = pooled * Wfc^T + b (fp32)
   }
 
   // ---- classifier backward (to the input) -----------------------------------------------------
@@ -578,11 +587,11 @@ struct dp_engine {
     const Block& last = blocks.back();
     const int pl = last.hout * last.hout;
     void *GA = g[0], *GB = g[1], *GC = g[2], *GD = g[3];
-    PROF(this, "head_bwd", 2.0 * N * pl * last.cout * es, 2.0 * N * last.cout * K, st, {
-      dp::launch_fc_backward(dlog, fc_w, dpooled, N, last.cout, K, st);
+    gemm(N, last.cout, K, 3, fc_w, dlog, nullptr, 0.f, dpooled, st);           // dpooled = dlogits * Wfc (fp32)
+    PROF(this, "head_bwd", 2.0 * N * pl * last.cout * es, 0, st, {
       dp::launch_pool_grad_bcast(dpooled, GB, N, pl, last.cout, bf16, st);
       dp::launch_gn_relu_backward(GB, last.out, nullptr, GA, head_gn.gamma, head_gn.beta, head_stats, gn_partial, N, pl, last.cout, bf16, st);
-    }); KERNEL_OK(); launches += 4;
+    }); KERNEL_OK(); launches += 3;
     for (int bi = (int)blocks.size() - 1; bi >= 0; --bi) {
       Block& b = blocks[bi];
       const int lid = bi + 1;
