@@ -126,7 +126,7 @@ class ResNetV2(nn.Module):
         """The native engine for this model at image size `img` (created on first use)."""
         from .engine import Engine
         precision = precision or os.environ.get("DORPATCH_PRECISION", "bf16")
-        chunk = int(chunk or os.environ.get("DORPATCH_CHUNK", "64"))
+        chunk = int(chunk or os.environ.get("DORPATCH_CHUNK", "128"))
         key = (int(img), precision, chunk, torch.cuda.current_device() if torch.cuda.is_available() else -1)
         ent = self._engines.get(key)
         if ent is not None and (ent[1] != self._version or ent[0].max_images < max_images):
