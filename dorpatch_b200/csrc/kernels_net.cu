@@ -372,10 +372,11 @@ void launch_gn_relu_backward_2pass(const void* dy, const void* x, const void* ad
 //             slab was read microseconds earlier by the same SM): read x, dy (+addend), write dx.
 // ------------------------------------------------------------------------------------
 namespace gnc {
-constexpr int THREADS = 256;
+constexpr int THREADS = 256;        // default CTA size (two CTAs per SM)
+constexpr int MAX_THREADS = 512;    // CTA size when only one CTA fits per SM (big slabs): twice the warps / loads in flight
 constexpr int MAX_GPT = 4;                       // groups per thread (V / cpg when cpg < V)
 constexpr size_t HDR = 1024;                     // mbarrier + cluster partials + stats
-constexpr size_t TP_BYTES = (size_t)THREADS * MAX_GPT * 2 * sizeof(float);
+__host__ __device__ constexpr size_t tp_bytes(int threads) { return (size_t)threads * MAX_GPT * 2 * sizeof(float); }
 constexpr uint32_t BULK_CHUNK = 32768;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -430,7 +431,7 @@ __device__ __forceinline__ void cta_group_reduce(const float* a, const float* b,
   }
   __syncthreads();
   if (threadIdx.x < GN_GROUPS) {
-    const int g = threadIdx.x, rpi = THREADS / cols;
+    const int g = threadIdx.x, rpi = (int)blockDim.x / cols;
     int c_lo, c_hi, j;
     if (cpg >= V) { c_lo = g * (cpg / V); c_hi = c_lo + cpg / V; j = 0; }
     else { c_lo = g / gpt; c_hi = c_lo + 1; j = g % gpt; }
@@ -489,7 +490,7 @@ struct Pipe {
 }  // namespace gnc
 
 template <typename T>
-__global__ void __launch_bounds__(gnc::THREADS) gn_fwd_cluster_kernel(const T* __restrict__ x, T* __restrict__ y,
+__global__ void __launch_bounds__(gnc::MAX_THREADS) gn_fwd_cluster_kernel(const T* __restrict__ x, T* __restrict__ y,
                                                                        const float* __restrict__ gamma,
                                                                        const float* __restrict__ beta,
                                                                        float* __restrict__ stats, int N, int P, int C,
@@ -504,12 +505,12 @@ __global__ void __launch_bounds__(gnc::THREADS) gn_fwd_cluster_kernel(const T* _
   float* s_mean = reinterpret_cast<float*>(smem + 64 + 256);  // [32]
   float* s_rstd = s_mean + GN_GROUPS;                         // [32]
   float* tp = reinterpret_cast<float*>(smem + gnc::HDR);
-  unsigned char* slabs = smem + gnc::HDR + gnc::TP_BYTES;
+  unsigned char* slabs = smem + gnc::HDR + gnc::tp_bytes((int)blockDim.x);
 
   const int p0 = (int)(((long long)P * rank) / CL), p1 = (int)(((long long)P * (rank + 1)) / CL);
   const int rows = p1 - p0;
   const uint32_t slab_bytes = (uint32_t)((size_t)rows * C * sizeof(T));
-  const int cols = C / V, rpi = gnc::THREADS / cols, cpg = C / GN_GROUPS;
+  const int cols = C / V, rpi = (int)blockDim.x / cols, cpg = C / GN_GROUPS;
   const int tcol = threadIdx.x % cols, trow = threadIdx.x / cols;
   pipe.init();
 
@@ -583,7 +584,7 @@ __global__ void __launch_bounds__(gnc::THREADS) gn_fwd_cluster_kernel(const T* _
 
 // UG: all V channels of a thread share one GroupNorm group (cpg >= V) -> per-group scalars
 template <typename T, bool UG>
-__global__ void __launch_bounds__(gnc::THREADS, 2) gn_bwd_cluster_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+__global__ void __launch_bounds__(gnc::MAX_THREADS, 1) gn_bwd_cluster_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                                           const T* __restrict__ addend, T* __restrict__ dx,
                                                                           const float* __restrict__ gamma,
                                                                           const float* __restrict__ beta,
@@ -601,12 +602,12 @@ __global__ void __launch_bounds__(gnc::THREADS, 2) gn_bwd_cluster_kernel(const T
   float* s_1 = reinterpret_cast<float*>(smem + 64 + 256);
   float* s_2 = s_1 + GN_GROUPS;
   float* tp = reinterpret_cast<float*>(smem + gnc::HDR);
-  unsigned char* slabs = smem + gnc::HDR + gnc::TP_BYTES;
+  unsigned char* slabs = smem + gnc::HDR + gnc::tp_bytes((int)blockDim.x);
 
   const int p0 = (int)(((long long)P * rank) / CL), p1 = (int)(((long long)P * (rank + 1)) / CL);
   const int rows = p1 - p0;
   const uint32_t slab_bytes = (uint32_t)((size_t)rows * C * sizeof(T));
-  const int cols = C / V, rpi = gnc::THREADS / cols, cpg = C / GN_GROUPS;
+  const int cols = C / V, rpi = (int)blockDim.x / cols, cpg = C / GN_GROUPS;
   const int tcol = threadIdx.x % cols, trow = threadIdx.x / cols;
   float ga[V];
 #pragma unroll
@@ -725,7 +726,7 @@ __global__ void __launch_bounds__(gnc::THREADS, 2) gn_bwd_cluster_kernel(const T
 // no global-load latency chains in either pass).  One cluster per sample; used when two slabs fit the
 // per-CTA budget.
 template <typename T, bool UG>
-__global__ void __launch_bounds__(gnc::THREADS, 2) gn_bwd_cluster_smem_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+__global__ void __launch_bounds__(gnc::MAX_THREADS, 1) gn_bwd_cluster_smem_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                                                const T* __restrict__ addend, T* __restrict__ dx,
                                                                                const float* __restrict__ gamma,
                                                                                const float* __restrict__ beta,
@@ -742,13 +743,13 @@ __global__ void __launch_bounds__(gnc::THREADS, 2) gn_bwd_cluster_smem_kernel(co
   float* s_1 = reinterpret_cast<float*>(smem + 64 + 256);
   float* s_2 = s_1 + GN_GROUPS;
   float* tp = reinterpret_cast<float*>(smem + gnc::HDR);
-  unsigned char* slabs = smem + gnc::HDR + gnc::TP_BYTES;
+  unsigned char* slabs = smem + gnc::HDR + gnc::tp_bytes((int)blockDim.x);
 
   const int p0 = (int)(((long long)P * rank) / CL), p1 = (int)(((long long)P * (rank + 1)) / CL);
   const int rows = p1 - p0;
   const uint32_t slab_bytes = (uint32_t)((size_t)rows * C * sizeof(T));
   const size_t base = ((size_t)n * P + p0) * C;
-  const int cols = C / V, rpi = gnc::THREADS / cols, cpg = C / GN_GROUPS;
+  const int cols = C / V, rpi = (int)blockDim.x / cols, cpg = C / GN_GROUPS;
   const int tcol = threadIdx.x % cols, trow = threadIdx.x / cols;
   pipe.init();
   if (threadIdx.x == 0) {
@@ -829,33 +830,38 @@ __global__ void __launch_bounds__(gnc::THREADS, 2) gn_bwd_cluster_smem_kernel(co
   cluster.barrier_wait();
 }
 
-struct GnPlan { int cl; int nbuf; size_t smem; uint32_t slab_stride; int ctas_per_sm; bool persistent; };
+struct GnPlan { int cl; int nbuf; size_t smem; uint32_t slab_stride; int ctas_per_sm; bool persistent; int threads; };
 // Tunables (environment, read once): DORPATCH_GN=twopass disables the cluster kernels;
 // DORPATCH_GN_PERSIST=1 -> persistent clusters with double-buffered slab prefetch (measured slower on
 // B200 than one cluster per sample: fewer resident CTAs); DORPATCH_GN_SOFT=<KB> per-CTA smem budget
 // used to pick the cluster size.
 static bool gn_plan(int P, int C, size_t es, GnPlan* out) {
-  static int mode = -1, persist = 0;
+  static int mode = -1, persist = 0, big_threads = gnc::MAX_THREADS;
   static size_t soft = 111 * 1024;
   if (mode < 0) {
     const char* e = getenv("DORPATCH_GN"); mode = (e && strcmp(e, "twopass") == 0) ? 0 : 1;
     if (const char* p = getenv("DORPATCH_GN_PERSIST")) persist = atoi(p);
     if (const char* q = getenv("DORPATCH_GN_SOFT")) soft = (size_t)atoi(q) * 1024;
+    if (const char* t = getenv("DORPATCH_GN_BIGTHREADS")) big_threads = atoi(t);
   }
   if (!mode) return false;
   if (C / (int)(16 / es) > gnc::THREADS) return false;
-  const size_t fixed = gnc::HDR + gnc::TP_BYTES, hard = 220 * 1024;
+  const size_t fixed = gnc::HDR + gnc::tp_bytes(gnc::THREADS), fixed_big = gnc::HDR + gnc::tp_bytes(big_threads), hard = 220 * 1024;
   for (int cl = 1; cl <= 8; cl *= 2) {
     if (cl > P) break;
     const size_t slab = (((size_t)((P + cl - 1) / cl)) * C * es + 127) / 128 * 128;
     if (persist) {
-      if (fixed + 2 * slab <= soft) { *out = GnPlan{cl, 2, fixed + 2 * slab, (uint32_t)slab, (int)(hard / (fixed + 2 * slab)), true}; return true; }
+      if (fixed + 2 * slab <= soft) { *out = GnPlan{cl, 2, fixed + 2 * slab, (uint32_t)slab, (int)(hard / (fixed + 2 * slab)), true, gnc::THREADS}; return true; }
       if (cl == 8) {
-        if (fixed + 2 * slab <= hard) { *out = GnPlan{cl, 2, fixed + 2 * slab, (uint32_t)slab, 1, true}; return true; }
-        if (fixed + slab <= hard) { *out = GnPlan{cl, 1, fixed + slab, (uint32_t)slab, 1, true}; return true; }
+        if (fixed + 2 * slab <= hard) { *out = GnPlan{cl, 2, fixed + 2 * slab, (uint32_t)slab, 1, true, gnc::THREADS}; return true; }
+        if (fixed + slab <= hard) { *out = GnPlan{cl, 1, fixed + slab, (uint32_t)slab, 1, true, gnc::THREADS}; return true; }
       }
-    } else if (fixed + slab <= soft || (cl == 8 && fixed + slab <= hard)) {
-      *out = GnPlan{cl, 1, fixed + slab, (uint32_t)slab, 1, false};
+    } else if (fixed + slab <= soft) {
+      *out = GnPlan{cl, 1, fixed + slab, (uint32_t)slab, 1, false, gnc::THREADS};
+      return true;
+    } else if (cl == 8 && fixed_big + slab <= hard) {
+      // a slab that leaves room for only one CTA per SM gets a 512-thread CTA
+      *out = GnPlan{cl, 1, fixed_big + slab, (uint32_t)slab, 1, false, big_threads};
       return true;
     }
   }
@@ -872,11 +878,11 @@ static int gn_grid(const GnPlan& pl, int N) {
 }
 
 template <typename K, typename... Args>
-static bool launch_cluster(K kernel, int cl, int nblocks, size_t smem, cudaStream_t st, Args... args) {
+static bool launch_cluster(K kernel, int cl, int nblocks, int threads, size_t smem, cudaStream_t st, Args... args) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(nblocks);
-  cfg.blockDim = dim3(gnc::THREADS);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1125,8 +1131,8 @@ void launch_gn_relu_forward(const void* x, void* y, const float* gamma, const fl
   if (gn_plan(P, C, bf16 ? 2 : 4, &pl)) {
     const int grid = gn_grid(pl, N);
     bool ok;
-    if (bf16) ok = launch_cluster(gn_fwd_cluster_kernel<__nv_bfloat16>, pl.cl, grid, pl.smem, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, stats, N, P, C, pl.nbuf, pl.slab_stride);
-    else ok = launch_cluster(gn_fwd_cluster_kernel<float>, pl.cl, grid, pl.smem, st, (const float*)x, (float*)y, gamma, beta, stats, N, P, C, pl.nbuf, pl.slab_stride);
+    if (bf16) ok = launch_cluster(gn_fwd_cluster_kernel<__nv_bfloat16>, pl.cl, grid, pl.threads, pl.smem, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, stats, N, P, C, pl.nbuf, pl.slab_stride);
+    else ok = launch_cluster(gn_fwd_cluster_kernel<float>, pl.cl, grid, pl.threads, pl.smem, st, (const float*)x, (float*)y, gamma, beta, stats, N, P, C, pl.nbuf, pl.slab_stride);
     if (ok) return;
     cudaGetLastError();   // clear and fall back
   }
@@ -1141,14 +1147,14 @@ void launch_gn_relu_backward(const void* dy, const void* x, const void* addend, 
   {   // both slabs in shared memory when they fit (DORPATCH_GN_DYSMEM=0 disables)
     static int dys = -1;
     if (dys < 0) { const char* e = getenv("DORPATCH_GN_DYSMEM"); dys = e ? atoi(e) : 1; }
-    const size_t es = bf16 ? 2 : 4, fixed = gnc::HDR + gnc::TP_BYTES;
+    const size_t es = bf16 ? 2 : 4, fixed = gnc::HDR + gnc::tp_bytes(gnc::THREADS);
     if (dys && gn_plan(P, C, es, &pl) && !pl.persistent && C / (int)(16 / es) <= gnc::THREADS) {
       for (int cl = 1; cl <= 8; cl *= 2) {
         if (cl > P) break;
         const size_t slab = (((size_t)((P + cl - 1) / cl)) * C * es + 127) / 128 * 128;
         if (fixed + 2 * slab <= 111 * 1024) {
           bool ok;
-#define GNS(TT, UGV) launch_cluster(gn_bwd_cluster_smem_kernel<TT, UGV>, cl, cl * N, fixed + 2 * slab, st, (const TT*)dy, (const TT*)x, (const TT*)addend, (TT*)dx, gamma, beta, stats, P, C, (uint32_t)slab)
+#define GNS(TT, UGV) launch_cluster(gn_bwd_cluster_smem_kernel<TT, UGV>, cl, cl * N, gnc::THREADS, fixed + 2 * slab, st, (const TT*)dy, (const TT*)x, (const TT*)addend, (TT*)dx, gamma, beta, stats, P, C, (uint32_t)slab)
           if (bf16) ok = ug ? GNS(__nv_bfloat16, true) : GNS(__nv_bfloat16, false);
           else ok = ug ? GNS(float, true) : GNS(float, false);
 #undef GNS
@@ -1162,7 +1168,7 @@ void launch_gn_relu_backward(const void* dy, const void* x, const void* addend, 
   if (gn_plan(P, C, bf16 ? 2 : 4, &pl)) {
     const int grid = gn_grid(pl, N);
     bool ok;
-#define GNB(TT, UGV) launch_cluster(gn_bwd_cluster_kernel<TT, UGV>, pl.cl, grid, pl.smem, st, (const TT*)dy, (const TT*)x, (const TT*)addend, (TT*)dx, gamma, beta, stats, N, P, C, pl.nbuf, pl.slab_stride)
+#define GNB(TT, UGV) launch_cluster(gn_bwd_cluster_kernel<TT, UGV>, pl.cl, grid, pl.threads, pl.smem, st, (const TT*)dy, (const TT*)x, (const TT*)addend, (TT*)dx, gamma, beta, stats, N, P, C, pl.nbuf, pl.slab_stride)
     if (bf16) ok = ug ? GNB(__nv_bfloat16, true) : GNB(__nv_bfloat16, false);
     else ok = ug ? GNB(float, true) : GNB(float, false);
 #undef GNB
