@@ -928,9 +928,18 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, i
         if (f[k] > best[k]) { best[k] = f[k]; bi[k] = ky * 3 + kx; }
     }
   Vec<T> o; o.pack(best); o.store(y + i * V);
-  if (amax != nullptr) {
+  if (amax != nullptr) {   // V argmax bytes packed into one 4- / 8-byte store
+    if (V == 8) {
+      uint2 pk;
+      pk.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+      pk.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+      *reinterpret_cast<uint2*>(amax + i * V) = pk;
+    } else {
+      uint32_t pk = 0;
 #pragma unroll
-    for (int k = 0; k < V; ++k) amax[i * V + k] = (int8_t)bi[k];
+      for (int k = 0; k < V; ++k) pk |= (uint32_t)bi[k] << (8 * k);
+      *reinterpret_cast<uint32_t*>(amax + i * V) = pk;
+    }
   }
 }
 
@@ -962,9 +971,12 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const int8_t* __res
       Vec<T> v; v.load(dy + o);
       float f[V]; v.unpack(f);
       const int want = ky * 3 + kx;
+      uint32_t am[2] = {0u, 0u};
+      if (V == 8) { const uint2 pk = *reinterpret_cast<const uint2*>(amax + o); am[0] = pk.x; am[1] = pk.y; }
+      else am[0] = *reinterpret_cast<const uint32_t*>(amax + o);
 #pragma unroll
       for (int k = 0; k < V; ++k)
-        if (amax[o + k] == want) acc[k] += f[k];
+        if ((int)((am[k >> 2] >> (8 * (k & 3))) & 0xffu) == want) acc[k] += f[k];
     }
   }
   Vec<T> out; out.pack(acc); out.store(dx + i * V);
