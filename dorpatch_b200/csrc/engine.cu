@@ -582,7 +582,15 @@ struct dp_engine {
 
   // ---- classifier backward (to the input) -----------------------------------------------------
   // dlog: [N,K] fp32 dev.  Leaves d/d(input) in `d_input` ([N,H,H,Cp] T).
-  void backward(int N, const float* dlog, cudaStream_t st) {
+  // `fused`: non-null -> finish with the fused stem-dgrad + masked EOT reduce into fused->G instead of
+  // producing d_input (bf16 own-stem path; the per-sample input gradient is never materialised).
+  struct FusedReduce { const int16_t* rects; float* G; int B, S, n0; };
+  bool stem_bwd_fused_ok() const {
+    static int en = -1;
+    if (en < 0) { const char* e = getenv("DORPATCH_STEM_BWD"); en = (e && strcmp(e, "cudnn") == 0) ? 0 : 1; }
+    return own_stem && en;
+  }
+  void backward(int N, const float* dlog, cudaStream_t st, const FusedReduce* fused = nullptr) {
     CUDNN_OK(cudnnSetStream(cudnn, st));
     const Block& last = blocks.back();
     const int pl = last.hout * last.hout;
@@ -623,6 +631,14 @@ struct dp_engine {
     const int hs = Hs();
     PROF(this, "maxpool_bwd", (double)N * (hs * hs + (hs / 2) * (hs / 2)) * STEM_CH * es, 0, st,
          dp::launch_maxpool_backward(GA, pool_amax, GB, N, hs, hs, STEM_CH, bf16, st)); KERNEL_OK(); ++launches;
+    if (fused != nullptr) {
+      PROF(this, "stem_bwd_reduce", (double)N * hs * hs * STEM_CH * es + 3.0 * H * H * 4 * (double)N / fused->S,
+           2.0 * N * hs * hs * STEM_CH * 147, st,
+           dp::launch_stem_bwd_reduce(GB, stem.w, stem.cin_pad, fused->rects, fused->G, fused->B, fused->S, fused->n0, N, H, H, st));
+      KERNEL_OK(); ++launches;
+      d_input = nullptr;
+      return;
+    }
     for (int n0 = 0; n0 < N; n0 += STEM_SUB) {
       const int n = std::min(STEM_SUB, N - n0);
       conv_bwd(0, stem, n, H, hs, (const char*)GB + (size_t)n0 * hs * hs * STEM_CH * es, (char*)GC + (size_t)n0 * H * H * Cpd * es, st);
@@ -907,7 +923,10 @@ static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t
     PROF(e, "cw_k4", 2.0 * n * e->K * 4, 0, st,
          dp::launch_cw(e->logits, e->y_d + n0, e->tg_d + n0, a->confidence, inv_s, e->loss_d + n0, e->preds_d + n0, e->dlogits, n, e->K, st));
     KERNEL_OK(); ++e->launches;
-    e->backward(n, e->dlogits, st);
+    const bool fuse = !xf_bytes && e->stem_bwd_fused_ok();
+    dp_engine::FusedReduce fr{rects, a->grad_adv, B, S, n0};
+    e->backward(n, e->dlogits, st, fuse ? &fr : nullptr);
+    if (fuse) continue;
     if (xf_bytes) {
       PROF(e, "reduce_affine", (double)n * H * H * 3 * e->es + 3.0 * H * H * 4 * (double)n / S, 0, st,
            dp::launch_reduce_affine(e->d_input, e->adv_x, e->xf_d, rects, a->grad_adv, S, n0, n, H, H, e->Cpd, e->bf16, st));

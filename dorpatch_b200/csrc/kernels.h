@@ -47,6 +47,9 @@ void launch_subsample2_adjoint_add(const void* dy, void* dx, int N, int H, int W
 // ---- hand-written bf16 tensor-core stem convolution on the tight C=3 input (kernels_stem.cu)
 void launch_stem_pack(const void* w_krsc, void* w_kn, int cin_pad, cudaStream_t st);
 void launch_stem_forward(const void* in, const void* w_kn, void* out, int N, int H, int W, cudaStream_t st);
+// stem dgrad fused with the masked EOT reduce: G[b] (+)= 2 * sum_s keep_s * dX_s, dX never materialised
+void launch_stem_bwd_reduce(const void* dY, const void* w_krsc, int cin_pad, const int16_t* rects, float* G, int B, int S,
+                            int n0, int n, int H, int W, cudaStream_t st);
 
 // ---- patch-side kernels (kernels_patch.cu) -------------------------------------------
 // utils.clip + add: adv_x = x + min(eps/||m(p-x)||,1) * m(p-x); l2[b], scale[b] dev outputs.

@@ -129,4 +129,157 @@ void launch_stem_forward(const void* in, const void* w_kn, void* out, int N, int
   stem_fwd_kernel<<<grid, stem::THREADS, stem::SMEM, st>>>((const __nv_bfloat16*)in, (const __nv_bfloat16*)w_kn, (__nv_bfloat16*)out, H, W);
 }
 
+
+// =====================================================================================================
+// Stem backward fused with the masked EOT reduce (K1^T):
+//   G[b,c,y,x] (+)= 2 * sum_{samples n of image b} keep_n(y,x) * dX_n[y,x,c],
+//   dX_n[y,x,c] = sum_{k,ky,kx} dY_n[(y+3-ky)/2, (x+3-kx)/2, k] * W[k,ky,kx,c]   (only parities that divide)
+// The per-sample input gradient [N,H,W,3] is never written: a CTA owns an 8x16 tile of input pixels of ONE
+// parity class (y%2, x%2) of ONE image, loops over that image's samples (cp.async double-buffered dY patches),
+// runs mma.sync m16n8k16 (N = 8 padded output channels, K = taps x 64) per sample and adds the result into
+// register accumulators under the sample's occlusion mask.  Replaces cuDNN's stem dgrad (2.6 ms/step incl. its
+// padding / folding helper kernels, writing a C-padded-to-8 gradient tensor) + reduce_kernel.
+// =====================================================================================================
+namespace stemb {
+constexpr int TI = 8, TJ = 16;                 // positions (i, j) = (y >> 1, x >> 1) per tile
+constexpr int PR = TI + 3, PC = TJ + 3;        // dY patch (rows i0-1 .. i0+TI+1)
+constexpr int PIX = 144;                       // bytes per patch pixel (128 + 16 pad: conflict-free ldmatrix)
+constexpr int THREADS = 256;
+constexpr int MAXTAPS = 16;
+constexpr size_t W_BYTES = (size_t)MAXTAPS * 64 * 16;
+constexpr size_t PATCH_BYTES = (size_t)PR * PC * PIX;
+constexpr size_t SMEM = W_BYTES + 2 * PATCH_BYTES;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(a));
+}
+__device__ __forceinline__ bool rect_hit(const short* r, int row, int col) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (row >= r[4 * k] && row < r[4 * k + 1] && col >= r[4 * k + 2] && col < r[4 * k + 3]) return true;
+  return false;
+}
+}  // namespace stemb
+
+// dY: [n, Ho, Wo, 64] bf16 for the chunk's samples (sample index relative to n0); w_krsc: [64][7][7][cin_pad] bf16.
+__global__ void __launch_bounds__(stemb::THREADS, 2) stem_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dY,
+                                                                             const __nv_bfloat16* __restrict__ w_krsc,
+                                                                             int cin_pad, const int16_t* __restrict__ rects,
+                                                                             float* __restrict__ G, int S, int n0, int n,
+                                                                             int H, int W) {
+  using namespace stemb;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* Ws = smem_raw;                                   // [tap][k][8] bf16, 16 B per (tap, k)
+  unsigned char* patch = smem_raw + W_BYTES;                      // [2][PR][PC][PIX]
+  const int Ho = H / 2, Wo = W / 2, Hc = H / 2, Wc = W / 2;       // positions per parity class
+  const int tiles_j = (Wc + TJ - 1) / TJ;
+  const int ti = blockIdx.x / tiles_j, tj = blockIdx.x % tiles_j;
+  const int py = blockIdx.y >> 1, px = blockIdx.y & 1;
+  const int b = n0 / S + blockIdx.z;
+  const int lo = max(n0, b * S), hi = min(n0 + n, (b + 1) * S);
+  if (lo >= hi) return;
+  const int i0 = ti * TI, j0 = tj * TJ;
+  const int nky = py ? 4 : 3, nkx = px ? 4 : 3, ntaps = nky * nkx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // class weights: tap t = a*nkx + c2 with ky = (py?0:1) + 2a, kx = (px?0:1) + 2c2
+  for (int q = threadIdx.x; q < ntaps * 64; q += THREADS) {
+    const int t = q >> 6, k = q & 63;
+    const int ky = (py ? 0 : 1) + 2 * (t / nkx), kx = (px ? 0 : 1) + 2 * (t % nkx);
+    const __nv_bfloat16* src = w_krsc + ((size_t)(k * 7 + ky) * 7 + kx) * cin_pad;
+    __nv_bfloat16 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = (c < 3) ? src[c] : __float2bfloat16(0.f);
+    *reinterpret_cast<uint4*>(Ws + (size_t)q * 16) = *reinterpret_cast<const uint4*>(v);
+  }
+
+  auto load_patch = [&](int sample, int buf) {
+    const __nv_bfloat16* src = dY + (size_t)(sample - n0) * Ho * Wo * 64;
+    unsigned char* dst = patch + (size_t)buf * PATCH_BYTES;
+    for (int q = threadIdx.x; q < PR * PC * 8; q += THREADS) {
+      const int pix = q >> 3, ch = q & 7;
+      const int oy = i0 - 1 + pix / PC, ox = j0 - 1 + pix % PC;
+      unsigned char* d = dst + (size_t)pix * PIX + ch * 16;
+      if (oy >= 0 && oy < Ho && ox >= 0 && ox < Wo) cp_async16(d, src + ((size_t)oy * Wo + ox) * 64 + ch * 8);
+      else *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    cp_commit();
+  };
+
+  float tot[4] = {0.f, 0.f, 0.f, 0.f};
+  const int g = lane >> 2, t4 = lane & 3;
+  const int irow = i0 + warp;                                      // this warp's position row
+  const int y = 2 * irow + py;
+  const int xA = 2 * (j0 + g) + px, xB = 2 * (j0 + g + 8) + px;   // the two position columns of this thread's C rows
+
+  load_patch(lo, 0);
+  for (int s = lo; s < hi; ++s) {
+    const int buf = (s - lo) & 1;
+    if (s + 1 < hi) { load_patch(s + 1, buf ^ 1); cp_wait<1>(); } else { cp_wait<0>(); }
+    __syncthreads();
+    const unsigned char* pb = patch + (size_t)buf * PATCH_BYTES;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < ntaps; ++t) {
+      const int a = t / nkx, c2 = t % nkx;
+      const int di = (py ? 2 : 1) - a, dj = (px ? 2 : 1) - c2;    // oy = i + di, ox = j + dj
+      const unsigned char* arow = pb + ((size_t)(warp + di + 1) * PC + (lane & 15) + dj + 1) * PIX + (lane >> 4) * 16;
+      const unsigned char* brow = Ws + ((size_t)t * 64 + (lane & 7) + ((lane >> 3) & 1) * 8) * 16;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t a0, a1, a2, a3, b0, b1;
+        stem::ldmatrix_x4(a0, a1, a2, a3, arow + kk * 32);
+        ldmatrix_x2_trans(b0, b1, brow + (size_t)kk * 16 * 16);
+        stem::mma_bf16(acc, a0, a1, a2, a3, b0, b1);
+      }
+    }
+    // occlusion mask of this sample at the thread's two pixels
+    short r[16];
+    bool keepA = true, keepB = true;
+    if (rects != nullptr) {
+      const int4* rp = reinterpret_cast<const int4*>(rects + (size_t)s * 16);
+      *reinterpret_cast<int4*>(r) = __ldg(rp);
+      *reinterpret_cast<int4*>(r + 8) = __ldg(rp + 1);
+      keepA = !rect_hit(r, y, xA);
+      keepB = !rect_hit(r, y, xB);
+    }
+    if (keepA) { tot[0] += acc[0]; tot[1] += acc[1]; }
+    if (keepB) { tot[2] += acc[2]; tot[3] += acc[3]; }
+    __syncthreads();                                               // patch[buf] may be refilled two iterations on
+  }
+  // C fragment: (row g: cols 2*t4, 2*t4+1), (row g+8: same cols); channels 0..2 are real
+  const bool first = (lo == b * S);
+  if (irow < Hc && t4 < 2) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int x = half ? xB : xA;
+      if (x >= W) continue;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = 2 * t4 + e;
+        if (c >= 3) continue;
+        float* gp = G + ((size_t)b * 3 + c) * H * W + (size_t)y * W + x;
+        const float v = 2.0f * tot[half * 2 + e];
+        *gp = first ? v : (*gp + v);
+      }
+    }
+  }
+}
+
+void launch_stem_bwd_reduce(const void* dY, const void* w_krsc, int cin_pad, const int16_t* rects, float* G, int B, int S,
+                            int n0, int n, int H, int W, cudaStream_t st) {
+  (void)B;
+  cudaFuncSetAttribute(stem_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stemb::SMEM);
+  const int nb = (n0 + n - 1) / S - n0 / S + 1;
+  const int tiles = ((H / 2 + stemb::TI - 1) / stemb::TI) * ((W / 2 + stemb::TJ - 1) / stemb::TJ);
+  stem_bwd_reduce_kernel<<<dim3(tiles, 4, nb), stemb::THREADS, stemb::SMEM, st>>>(
+      (const __nv_bfloat16*)dY, (const __nv_bfloat16*)w_krsc, cin_pad, rects, G, S, n0, n, H, W);
+}
+
 }  // namespace dp
