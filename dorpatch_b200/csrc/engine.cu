@@ -585,11 +585,8 @@ struct dp_engine {
   // `fused`: non-null -> finish with the fused stem-dgrad + masked EOT reduce into fused->G instead of
   // producing d_input (bf16 own-stem path; the per-sample input gradient is never materialised).
   struct FusedReduce { const int16_t* rects; float* G; int B, S, n0; };
-  bool stem_bwd_fused_ok() const {
-    static int en = -1;
-    if (en < 0) { const char* e = getenv("DORPATCH_STEM_BWD"); en = (e && strcmp(e, "cudnn") == 0) ? 0 : 1; }
-    return own_stem && en;
-  }
+  bool fused_stem_bwd = false;     // set at create: own_stem && DORPATCH_STEM_BWD != "cudnn"
+  bool stem_bwd_fused_ok() const { return fused_stem_bwd; }
   void backward(int N, const float* dlog, cudaStream_t st, const FusedReduce* fused = nullptr) {
     CUDNN_OK(cudnnSetStream(cudnn, st));
     const Block& last = blocks.back();
@@ -709,6 +706,8 @@ int32_t dp_engine_create(const dp_config* cfg, dp_engine** out) {
     const char* stem_env = getenv("DORPATCH_STEM");
     e->own_stem = e->bf16 && !(stem_env && strcmp(stem_env, "cudnn") == 0);
     e->Cp = e->own_stem ? 3 : e->Cpd;
+    const char* sb_env = getenv("DORPATCH_STEM_BWD");
+    e->fused_stem_bwd = e->own_stem && !(sb_env && strcmp(sb_env, "cudnn") == 0);
     e->H = cfg->img; e->K = cfg->n_classes; e->chunk = cfg->chunk;
     e->cudnn_dt = e->bf16 ? CUDNN_DATA_BFLOAT16 : CUDNN_DATA_FLOAT;
     e->cuda_dt = e->bf16 ? CUDA_R_16BF : CUDA_R_32F;
