@@ -844,6 +844,19 @@ int32_t dp_expand(dp_engine* e, const float* img, int32_t B, int32_t S, const in
   DP_CATCH
 }
 
+int32_t dp_expand_dev(dp_engine* e, const float* img, int32_t B, int32_t S, const int16_t* rects_dev, void* out, void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  if (!out) fail("dp_expand_dev needs an output buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  const int N = B * S;
+  PROF(e, "expand_k1", (double)N * e->H * e->H * 3 * e->es + 3.0 * e->H * e->H * 4 * (double)B, 0, st,
+       dp::launch_expand(img, nullptr, nullptr, nullptr, nullptr, rects_dev, out, B, S, 0, N, e->H, e->H, e->Cp, e->bf16, false, e->num_sms, st));
+  KERNEL_OK(); ++e->launches;
+  DP_CATCH
+}
+
 int32_t dp_predict(dp_engine* e, const float* img, int32_t B, int32_t S, const int16_t* rects_host, int32_t* preds_host,
                    float* logits_host, void* stream) {
   DP_TRY

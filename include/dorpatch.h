@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DP_ABI_VERSION 3
+#define DP_ABI_VERSION 4
 
 enum dp_precision {
   DP_PREC_FP32 = 0, /* fp32 storage, fp32 FMA math (no tensor cores): parity checks   */
@@ -102,6 +102,10 @@ int32_t dp_window_sum(dp_engine* e, const float* t, int32_t B, int32_t k, int32_
  * are 0.5 in image space = exactly 0 after normalisation. */
 int32_t dp_expand(dp_engine* e, const float* img, int32_t B, int32_t S, const int16_t* rects_host,
                   void* out, void* stream);
+/* Same kernel with the rectangles already on the device (int16 [B*S][4][4] dev, or NULL): no host copy, no
+ * synchronisation -- exactly one kernel launch on `stream` (what bench.py brackets with CUDA events). */
+int32_t dp_expand_dev(dp_engine* e, const float* img, int32_t B, int32_t S, const int16_t* rects_dev,
+                      void* out, void* stream);
 int32_t dp_input_layout(const dp_engine* e, int32_t* c_pad, int32_t* elem_bytes);
 
 /* ---- forward-only: model(occlude(img)) ---------------------------------------------- */
