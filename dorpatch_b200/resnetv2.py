@@ -136,6 +136,8 @@ class ResNetV2(nn.Module):
             eng = Engine(img=img, n_classes=self.num_classes, precision=precision, chunk=chunk,
                          max_images=max(int(max_images), 1))
             eng.load_state_dict({k: v for k, v in self.state_dict().items()})
+            from . import runtime
+            runtime.register(eng)          # weight-free helpers (utils.clip, patch_selection) reuse it
             ent = (eng, self._version)
             self._engines[key] = ent
         return ent[0]
