@@ -971,12 +971,9 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ dy, const int8_t* __res
       Vec<T> v; v.load(dy + o);
       float f[V]; v.unpack(f);
       const int want = ky * 3 + kx;
-      uint32_t am[2] = {0u, 0u};
-      if (V == 8) { const uint2 pk = *reinterpret_cast<const uint2*>(amax + o); am[0] = pk.x; am[1] = pk.y; }
-      else am[0] = *reinterpret_cast<const uint32_t*>(amax + o);
 #pragma unroll
       for (int k = 0; k < V; ++k)
-        if ((int)((am[k >> 2] >> (8 * (k & 3))) & 0xffu) == want) acc[k] += f[k];
+        if (amax[o + k] == want) acc[k] += f[k];
     }
   }
   Vec<T> out; out.pack(acc); out.store(dx + i * V);

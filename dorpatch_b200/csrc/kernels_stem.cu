@@ -145,8 +145,8 @@ constexpr int TI = 8, TJ = 16;                 // positions (i, j) = (y >> 1, x 
 constexpr int PR = TI + 3, PC = TJ + 3;        // dY patch (rows i0-1 .. i0+TI+1)
 constexpr int PIX = 144;                       // bytes per patch pixel (128 + 16 pad: conflict-free ldmatrix)
 constexpr int THREADS = 256;
-constexpr int MAXTAPS = 16;
-constexpr size_t W_BYTES = (size_t)MAXTAPS * 64 * 16;
+constexpr int ALLTAPS = 49;                      // 9 + 12 + 12 + 16 taps of the four parity classes
+constexpr size_t W_BYTES = (size_t)ALLTAPS * 64 * 16;
 constexpr size_t PATCH_BYTES = (size_t)PR * PC * PIX;
 constexpr size_t SMEM = W_BYTES + 2 * PATCH_BYTES;
 
@@ -169,6 +169,8 @@ __device__ __forceinline__ bool rect_hit(const short* r, int row, int col) {
 }  // namespace stemb
 
 // dY: [n, Ho, Wo, 64] bf16 for the chunk's samples (sample index relative to n0); w_krsc: [64][7][7][cin_pad] bf16.
+// One CTA = one 8x16 tile of positions (i,j) of one image = a 16x32 block of input pixels; all four parity
+// classes share the dY patch (loaded once per sample).
 __global__ void __launch_bounds__(stemb::THREADS, 2) stem_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dY,
                                                                              const __nv_bfloat16* __restrict__ w_krsc,
                                                                              int cin_pad, const int16_t* __restrict__ rects,
@@ -176,23 +178,24 @@ __global__ void __launch_bounds__(stemb::THREADS, 2) stem_bwd_reduce_kernel(cons
                                                                              int H, int W) {
   using namespace stemb;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* Ws = smem_raw;                                   // [tap][k][8] bf16, 16 B per (tap, k)
+  unsigned char* Ws = smem_raw;                                   // [49 taps, class-major][k][8] bf16, 16 B per (tap, k)
   unsigned char* patch = smem_raw + W_BYTES;                      // [2][PR][PC][PIX]
   const int Ho = H / 2, Wo = W / 2, Hc = H / 2, Wc = W / 2;       // positions per parity class
   const int tiles_j = (Wc + TJ - 1) / TJ;
   const int ti = blockIdx.x / tiles_j, tj = blockIdx.x % tiles_j;
-  const int py = blockIdx.y >> 1, px = blockIdx.y & 1;
-  const int b = n0 / S + blockIdx.z;
+  const int b = n0 / S + blockIdx.y;
   const int lo = max(n0, b * S), hi = min(n0 + n, (b + 1) * S);
   if (lo >= hi) return;
   const int i0 = ti * TI, j0 = tj * TJ;
-  const int nky = py ? 4 : 3, nkx = px ? 4 : 3, ntaps = nky * nkx;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // class weights: tap t = a*nkx + c2 with ky = (py?0:1) + 2a, kx = (px?0:1) + 2c2
-  for (int q = threadIdx.x; q < ntaps * 64; q += THREADS) {
+  // weights, class-major: class cls = py*2+px owns taps [tap0(cls), tap0(cls) + nky*nkx): 9, 12, 12, 16 taps
+  for (int q = threadIdx.x; q < 49 * 64; q += THREADS) {
     const int t = q >> 6, k = q & 63;
-    const int ky = (py ? 0 : 1) + 2 * (t / nkx), kx = (px ? 0 : 1) + 2 * (t % nkx);
+    int cls = 0, tl = t;
+    if (tl >= 9) { cls = 1; tl -= 9; if (tl >= 12) { cls = 2; tl -= 12; if (tl >= 12) { cls = 3; tl -= 12; } } }
+    const int py = cls >> 1, px = cls & 1, nkx = px ? 4 : 3;
+    const int ky = (py ? 0 : 1) + 2 * (tl / nkx), kx = (px ? 0 : 1) + 2 * (tl % nkx);
     const __nv_bfloat16* src = w_krsc + ((size_t)(k * 7 + ky) * 7 + kx) * cin_pad;
     __nv_bfloat16 v[8];
 #pragma unroll
@@ -213,11 +216,11 @@ __global__ void __launch_bounds__(stemb::THREADS, 2) stem_bwd_reduce_kernel(cons
     cp_commit();
   };
 
-  float tot[4] = {0.f, 0.f, 0.f, 0.f};
+  float tot[4][4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { tot[c][0] = tot[c][1] = tot[c][2] = tot[c][3] = 0.f; }
   const int g = lane >> 2, t4 = lane & 3;
   const int irow = i0 + warp;                                      // this warp's position row
-  const int y = 2 * irow + py;
-  const int xA = 2 * (j0 + g) + px, xB = 2 * (j0 + g + 8) + px;   // the two position columns of this thread's C rows
 
   load_patch(lo, 0);
   for (int s = lo; s < hi; ++s) {
@@ -225,48 +228,59 @@ __global__ void __launch_bounds__(stemb::THREADS, 2) stem_bwd_reduce_kernel(cons
     if (s + 1 < hi) { load_patch(s + 1, buf ^ 1); cp_wait<1>(); } else { cp_wait<0>(); }
     __syncthreads();
     const unsigned char* pb = patch + (size_t)buf * PATCH_BYTES;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int t = 0; t < ntaps; ++t) {
-      const int a = t / nkx, c2 = t % nkx;
-      const int di = (py ? 2 : 1) - a, dj = (px ? 2 : 1) - c2;    // oy = i + di, ox = j + dj
-      const unsigned char* arow = pb + ((size_t)(warp + di + 1) * PC + (lane & 15) + dj + 1) * PIX + (lane >> 4) * 16;
-      const unsigned char* brow = Ws + ((size_t)t * 64 + (lane & 7) + ((lane >> 3) & 1) * 8) * 16;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        uint32_t a0, a1, a2, a3, b0, b1;
-        stem::ldmatrix_x4(a0, a1, a2, a3, arow + kk * 32);
-        ldmatrix_x2_trans(b0, b1, brow + (size_t)kk * 16 * 16);
-        stem::mma_bf16(acc, a0, a1, a2, a3, b0, b1);
-      }
-    }
-    // occlusion mask of this sample at the thread's two pixels
     short r[16];
-    bool keepA = true, keepB = true;
     if (rects != nullptr) {
       const int4* rp = reinterpret_cast<const int4*>(rects + (size_t)s * 16);
       *reinterpret_cast<int4*>(r) = __ldg(rp);
       *reinterpret_cast<int4*>(r + 8) = __ldg(rp + 1);
-      keepA = !rect_hit(r, y, xA);
-      keepB = !rect_hit(r, y, xB);
     }
-    if (keepA) { tot[0] += acc[0]; tot[1] += acc[1]; }
-    if (keepB) { tot[2] += acc[2]; tot[3] += acc[3]; }
+    int tap0 = 0;
+#pragma unroll
+    for (int cls = 0; cls < 4; ++cls) {
+      const int py = cls >> 1, px = cls & 1;
+      const int nky = py ? 4 : 3, nkx = px ? 4 : 3, ntaps = nky * nkx;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int t = 0; t < ntaps; ++t) {
+        const int a = t / nkx, c2 = t % nkx;
+        const int di = (py ? 2 : 1) - a, dj = (px ? 2 : 1) - c2;  // oy = i + di, ox = j + dj
+        const unsigned char* arow = pb + ((size_t)(warp + di + 1) * PC + (lane & 15) + dj + 1) * PIX + (lane >> 4) * 16;
+        const unsigned char* brow = Ws + ((size_t)(tap0 + t) * 64 + (lane & 7) + ((lane >> 3) & 1) * 8) * 16;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t a0, a1, a2, a3, b0, b1;
+          stem::ldmatrix_x4(a0, a1, a2, a3, arow + kk * 32);
+          ldmatrix_x2_trans(b0, b1, brow + (size_t)kk * 16 * 16);
+          stem::mma_bf16(acc, a0, a1, a2, a3, b0, b1);
+        }
+      }
+      tap0 += ntaps;
+      const int y = 2 * irow + py, xA = 2 * (j0 + g) + px, xB = 2 * (j0 + g + 8) + px;
+      const bool keepA = rects == nullptr || !rect_hit(r, y, xA);
+      const bool keepB = rects == nullptr || !rect_hit(r, y, xB);
+      if (keepA) { tot[cls][0] += acc[0]; tot[cls][1] += acc[1]; }
+      if (keepB) { tot[cls][2] += acc[2]; tot[cls][3] += acc[3]; }
+    }
     __syncthreads();                                               // patch[buf] may be refilled two iterations on
   }
   // C fragment: (row g: cols 2*t4, 2*t4+1), (row g+8: same cols); channels 0..2 are real
   const bool first = (lo == b * S);
   if (irow < Hc && t4 < 2) {
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int x = half ? xB : xA;
-      if (x >= W) continue;
+    for (int cls = 0; cls < 4; ++cls) {
+      const int py = cls >> 1, px = cls & 1;
+      const int y = 2 * irow + py;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int c = 2 * t4 + e;
-        if (c >= 3) continue;
-        float* gp = G + ((size_t)b * 3 + c) * H * W + (size_t)y * W + x;
-        const float v = 2.0f * tot[half * 2 + e];
-        *gp = first ? v : (*gp + v);
+      for (int half = 0; half < 2; ++half) {
+        const int x = 2 * (j0 + g + half * 8) + px;
+        if (x >= W) continue;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = 2 * t4 + e;
+          if (c >= 3) continue;
+          float* gp = G + ((size_t)b * 3 + c) * H * W + (size_t)y * W + x;
+          const float v = 2.0f * tot[cls][half * 2 + e];
+          *gp = first ? v : (*gp + v);
+        }
       }
     }
   }
@@ -278,7 +292,7 @@ void launch_stem_bwd_reduce(const void* dY, const void* w_krsc, int cin_pad, con
   cudaFuncSetAttribute(stem_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stemb::SMEM);
   const int nb = (n0 + n - 1) / S - n0 / S + 1;
   const int tiles = ((H / 2 + stemb::TI - 1) / stemb::TI) * ((W / 2 + stemb::TJ - 1) / stemb::TJ);
-  stem_bwd_reduce_kernel<<<dim3(tiles, 4, nb), stemb::THREADS, stemb::SMEM, st>>>(
+  stem_bwd_reduce_kernel<<<dim3(tiles, nb), stemb::THREADS, stemb::SMEM, st>>>(
       (const __nv_bfloat16*)dY, (const __nv_bfloat16*)w_krsc, cin_pad, rects, G, S, n0, n, H, W);
 }
 
