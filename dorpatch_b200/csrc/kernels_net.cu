@@ -836,13 +836,14 @@ struct GnPlan { int cl; int nbuf; size_t smem; uint32_t slab_stride; int ctas_pe
 // B200 than one cluster per sample: fewer resident CTAs); DORPATCH_GN_SOFT=<KB> per-CTA smem budget
 // used to pick the cluster size.
 static bool gn_plan(int P, int C, size_t es, GnPlan* out) {
-  static int mode = -1, persist = 0, big_threads = gnc::MAX_THREADS;
+  static int mode = -1, persist = 0, big_threads = gnc::MAX_THREADS, cl16 = 0;
   static size_t soft = 111 * 1024;
   if (mode < 0) {
     const char* e = getenv("DORPATCH_GN"); mode = (e && strcmp(e, "twopass") == 0) ? 0 : 1;
     if (const char* p = getenv("DORPATCH_GN_PERSIST")) persist = atoi(p);
     if (const char* q = getenv("DORPATCH_GN_SOFT")) soft = (size_t)atoi(q) * 1024;
     if (const char* t = getenv("DORPATCH_GN_BIGTHREADS")) big_threads = atoi(t);
+    if (const char* c = getenv("DORPATCH_GN_CL16")) cl16 = atoi(c);   // non-portable cluster size 16 for the biggest slabs
   }
   if (!mode) return false;
   if (C / (int)(16 / es) > gnc::THREADS) return false;
@@ -858,6 +859,10 @@ static bool gn_plan(int P, int C, size_t es, GnPlan* out) {
       }
     } else if (fixed + slab <= soft) {
       *out = GnPlan{cl, 1, fixed + slab, (uint32_t)slab, 1, false, gnc::THREADS};
+      return true;
+    } else if (cl == 8 && cl16 && P >= 16 && fixed + (slab + 1) / 2 + 128 <= soft) {
+      const size_t slab16 = (((size_t)((P + 15) / 16)) * C * es + 127) / 128 * 128;
+      *out = GnPlan{16, 1, fixed + slab16, (uint32_t)slab16, 1, false, gnc::THREADS};
       return true;
     } else if (cl == 8 && fixed_big + slab <= hard) {
       // a slab that leaves room for only one CTA per SM gets a 512-thread CTA
@@ -880,6 +885,7 @@ static int gn_grid(const GnPlan& pl, int N) {
 template <typename K, typename... Args>
 static bool launch_cluster(K kernel, int cl, int nblocks, int threads, size_t smem, cudaStream_t st, Args... args) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cl > 8) cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(nblocks);
   cfg.blockDim = dim3(threads);
