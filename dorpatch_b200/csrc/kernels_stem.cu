@@ -234,31 +234,41 @@ __global__ void __launch_bounds__(stemb::THREADS, 2) stem_bwd_reduce_kernel(cons
       *reinterpret_cast<int4*>(r) = __ldg(rp);
       *reinterpret_cast<int4*>(r + 8) = __ldg(rp + 1);
     }
-    int tap0 = 0;
+    // The 49 taps use only 16 distinct patch shifts (di, dj) in {-1..2}^2: load each A fragment once and feed
+    // every parity class that has a tap at this shift (shared-memory bandwidth is the limit: N is only 8).
+    float acc[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; }
+#pragma unroll
+    for (int di = -1; di <= 2; ++di) {
+#pragma unroll
+      for (int dj = -1; dj <= 2; ++dj) {
+        const unsigned char* arow = pb + ((size_t)(warp + di + 1) * PC + (lane & 15) + dj + 1) * PIX + (lane >> 4) * 16;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t a0, a1, a2, a3;
+          stem::ldmatrix_x4(a0, a1, a2, a3, arow + kk * 32);
+#pragma unroll
+          for (int cls = 0; cls < 4; ++cls) {
+            const int py = cls >> 1, px = cls & 1, nkx = px ? 4 : 3;
+            if ((di == 2 && !py) || (dj == 2 && !px)) continue;   // compile-time after unrolling
+            const int t = ((py ? 2 : 1) - di) * nkx + ((px ? 2 : 1) - dj);
+            const int tap0 = cls == 0 ? 0 : (cls == 1 ? 9 : (cls == 2 ? 21 : 33));
+            uint32_t b0, b1;
+            ldmatrix_x2_trans(b0, b1, Ws + ((size_t)(tap0 + t) * 64 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * 16);
+            stem::mma_bf16(acc[cls], a0, a1, a2, a3, b0, b1);
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int cls = 0; cls < 4; ++cls) {
       const int py = cls >> 1, px = cls & 1;
-      const int nky = py ? 4 : 3, nkx = px ? 4 : 3, ntaps = nky * nkx;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int t = 0; t < ntaps; ++t) {
-        const int a = t / nkx, c2 = t % nkx;
-        const int di = (py ? 2 : 1) - a, dj = (px ? 2 : 1) - c2;  // oy = i + di, ox = j + dj
-        const unsigned char* arow = pb + ((size_t)(warp + di + 1) * PC + (lane & 15) + dj + 1) * PIX + (lane >> 4) * 16;
-        const unsigned char* brow = Ws + ((size_t)(tap0 + t) * 64 + (lane & 7) + ((lane >> 3) & 1) * 8) * 16;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          uint32_t a0, a1, a2, a3, b0, b1;
-          stem::ldmatrix_x4(a0, a1, a2, a3, arow + kk * 32);
-          ldmatrix_x2_trans(b0, b1, brow + (size_t)kk * 16 * 16);
-          stem::mma_bf16(acc, a0, a1, a2, a3, b0, b1);
-        }
-      }
-      tap0 += ntaps;
       const int y = 2 * irow + py, xA = 2 * (j0 + g) + px, xB = 2 * (j0 + g + 8) + px;
       const bool keepA = rects == nullptr || !rect_hit(r, y, xA);
       const bool keepB = rects == nullptr || !rect_hit(r, y, xB);
-      if (keepA) { tot[cls][0] += acc[0]; tot[cls][1] += acc[1]; }
-      if (keepB) { tot[cls][2] += acc[2]; tot[cls][3] += acc[3]; }
+      if (keepA) { tot[cls][0] += acc[cls][0]; tot[cls][1] += acc[cls][1]; }
+      if (keepB) { tot[cls][2] += acc[cls][2]; tot[cls][3] += acc[cls][3]; }
     }
     __syncthreads();                                               // patch[buf] may be refilled two iterations on
   }
