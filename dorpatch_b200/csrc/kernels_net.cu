@@ -591,7 +591,10 @@ __global__ void __launch_bounds__(gnc::MAX_THREADS, 1) gn_bwd_cluster_kernel(con
                                                                           const float* __restrict__ stats, int N, int P, int C,
                                                                           int nbuf, uint32_t slab_stride) {
   constexpr int V = Vec<T>::N;
-  constexpr int U = 2;          // independent global loads in flight per thread (plus the TMA prefetch)
+#ifndef DP_GN_BWD_U
+#define DP_GN_BWD_U 4
+#endif
+  constexpr int U = DP_GN_BWD_U;   // independent global loads in flight per thread (plus the TMA slab)
   constexpr int GV = UG ? 1 : V;
   extern __shared__ __align__(128) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
