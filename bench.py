@@ -406,7 +406,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--precision", default=os.environ.get("DORPATCH_PRECISION", "bf16"), choices=["fp32", "tf32", "bf16"])
-    ap.add_argument("--chunk", type=int, default=int(os.environ.get("DORPATCH_CHUNK", "512")))
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("DORPATCH_CHUNK", "256")))
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--eot", type=int, default=S_PER_GPU)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

@@ -136,6 +136,36 @@ struct dp_engine {
   void* d_input = nullptr;         // result of backward: [n,H,H,Cp]
   void* lib_ws = nullptr; size_t lib_ws_bytes = 0;
 
+  // ---- lanes: complete per-chunk workspaces.  dp_attack_grad alternates its chunks between two lanes on
+  // two internal streams so that one chunk's kernel tails / memory-bound GroupNorm passes overlap the other
+  // chunk's tensor-core convolutions.  The members above (net_in, act, ..., Block::h1...) always alias the
+  // lane selected by use_lane(); launches capture the pointers at enqueue time, so switching between chunks is safe.
+  struct LaneBufs {
+    void *net_in = nullptr, *act = nullptr, *act2 = nullptr, *x0 = nullptr;
+    int8_t* pool_amax = nullptr;
+    void* g[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *gn_partial = nullptr, *head_stats = nullptr, *pooled = nullptr, *dpooled = nullptr, *logits = nullptr, *dlogits = nullptr;
+    void* lib_ws = nullptr;
+    std::vector<void*> h1, h2, out;
+    std::vector<float*> st1, st2, st3;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    cudnnHandle_t cudnn = nullptr;
+  };
+  std::vector<LaneBufs> lanes;
+  cudaEvent_t ev_prep = nullptr;
+  void use_lane(int l) {
+    LaneBufs& L = lanes[l];
+    net_in = L.net_in; act = L.act; act2 = L.act2; x0 = L.x0; pool_amax = L.pool_amax;
+    for (int i = 0; i < 4; ++i) g[i] = L.g[i];
+    gn_partial = L.gn_partial; head_stats = L.head_stats; pooled = L.pooled; dpooled = L.dpooled;
+    logits = L.logits; dlogits = L.dlogits; lib_ws = L.lib_ws; cudnn = L.cudnn;
+    for (size_t i = 0; i < blocks.size(); ++i) {
+      blocks[i].h1 = L.h1[i]; blocks[i].h2 = L.h2[i]; blocks[i].out = L.out[i];
+      blocks[i].st1 = L.st1[i]; blocks[i].st2 = L.st2[i]; blocks[i].st3 = L.st3[i];
+    }
+  }
+
   // per-image buffers (max_images)
   float* adv_x = nullptr; float* dLs = nullptr; float* scale = nullptr; float* l2 = nullptr;
   float* loss_struc = nullptr; float* loss_density = nullptr; float* group_lasso = nullptr;
@@ -278,31 +308,47 @@ struct dp_engine {
       make_conv(b.c1, b.cin, b.mid, 1, 1, 0, b.cin);
       make_conv(b.c2, b.mid, b.mid, 3, b.stride, 1, b.mid);
       make_conv(b.c3, b.mid, b.cout, 1, 1, 0, b.mid);
-      b.h1 = dmalloc(n * b.hin * b.hin * b.mid * es);
-      b.h2 = dmalloc(n * b.hout * b.hout * b.mid * es);
-      b.out = dmalloc(n * b.hout * b.hout * b.cout * es);
-      b.st1 = (float*)dmalloc(n * dp::GN_GROUPS * 2 * 4);
-      b.st2 = (float*)dmalloc(n * dp::GN_GROUPS * 2 * 4);
-      b.st3 = (float*)dmalloc(n * dp::GN_GROUPS * 2 * 4);
     }
     make_gn(head_gn, WIDTHS[3]);
     fc_w = (float*)dmalloc((size_t)K * WIDTHS[3] * 4);
     fc_b = (float*)dmalloc((size_t)K * 4);
     const size_t ma = max_act_elems();
-    net_in = dmalloc(n * H * H * Cp * es);
-    act = dmalloc(n * ma * es);
-    act2 = dmalloc(n * ma * es / 4 + 256);
-    x0 = dmalloc(n * Hp() * Hp() * STEM_CH * es);
-    pool_amax = (int8_t*)dmalloc(n * Hp() * Hp() * STEM_CH);
-    for (int i = 0; i < 4; ++i) g[i] = dmalloc(n * ma * es);
-    gn_partial = (float*)dmalloc(n * dp::GN_MAX_SPLITS * dp::GN_GROUPS * 2 * 4);
-    head_stats = (float*)dmalloc(n * dp::GN_GROUPS * 2 * 4);
-    pooled = (float*)dmalloc(n * WIDTHS[3] * 4);
-    dpooled = (float*)dmalloc(n * WIDTHS[3] * 4);
-    logits = (float*)dmalloc(n * K * 4);
-    dlogits = (float*)dmalloc(n * K * 4);
     lib_ws_bytes = (size_t)512 << 20;
-    lib_ws = dmalloc(lib_ws_bytes);
+    int n_lanes = 2;
+    if (const char* le = getenv("DORPATCH_LANES")) n_lanes = atoi(le);
+    if (n_lanes < 1) n_lanes = 1;
+    if (n_lanes > 2) n_lanes = 2;
+    lanes.resize(n_lanes);
+    CUDA_OK(cudaEventCreateWithFlags(&ev_prep, cudaEventDisableTiming));
+    for (int l = 0; l < n_lanes; ++l) {
+      LaneBufs& L = lanes[l];
+      for (auto& b : blocks) {
+        L.h1.push_back(dmalloc(n * b.hin * b.hin * b.mid * es));
+        L.h2.push_back(dmalloc(n * b.hout * b.hout * b.mid * es));
+        L.out.push_back(dmalloc(n * b.hout * b.hout * b.cout * es));
+        L.st1.push_back((float*)dmalloc(n * dp::GN_GROUPS * 2 * 4));
+        L.st2.push_back((float*)dmalloc(n * dp::GN_GROUPS * 2 * 4));
+        L.st3.push_back((float*)dmalloc(n * dp::GN_GROUPS * 2 * 4));
+      }
+      L.net_in = dmalloc(n * H * H * Cp * es);
+      L.act = dmalloc(n * ma * es);
+      L.act2 = dmalloc(n * ma * es / 4 + 256);
+      L.x0 = dmalloc(n * Hp() * Hp() * STEM_CH * es);
+      L.pool_amax = (int8_t*)dmalloc(n * Hp() * Hp() * STEM_CH);
+      for (int i = 0; i < 4; ++i) L.g[i] = dmalloc(n * ma * es);
+      L.gn_partial = (float*)dmalloc(n * dp::GN_MAX_SPLITS * dp::GN_GROUPS * 2 * 4);
+      L.head_stats = (float*)dmalloc(n * dp::GN_GROUPS * 2 * 4);
+      L.pooled = (float*)dmalloc(n * WIDTHS[3] * 4);
+      L.dpooled = (float*)dmalloc(n * WIDTHS[3] * 4);
+      L.logits = (float*)dmalloc(n * K * 4);
+      L.dlogits = (float*)dmalloc(n * K * 4);
+      L.lib_ws = dmalloc(lib_ws_bytes);
+      CUDA_OK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+      if (l == 0) L.cudnn = cudnn;
+      else CUDNN_OK(cudnnCreate(&L.cudnn));
+    }
+    use_lane(0);
     const size_t B = (size_t)cfg.max_images, HW = (size_t)H * H;
     adv_x = (float*)dmalloc(B * 3 * HW * 4);
     dLs = (float*)dmalloc(B * 3 * HW * 4);
@@ -746,6 +792,13 @@ void dp_engine_destroy(dp_engine* e) {
   for (auto& b : e->blocks) { kill(b.ds); kill(b.c1); kill(b.c2); kill(b.c3); }
   for (auto& r : e->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
+  for (size_t l = 0; l < e->lanes.size(); ++l) {
+    if (e->lanes[l].stream) cudaStreamDestroy(e->lanes[l].stream);
+    if (e->lanes[l].done) cudaEventDestroy(e->lanes[l].done);
+    if (l > 0 && e->lanes[l].cudnn) cudnnDestroy(e->lanes[l].cudnn);
+  }
+  if (!e->lanes.empty()) e->cudnn = e->lanes[0].cudnn;
+  if (e->ev_prep) cudaEventDestroy(e->ev_prep);
   for (void* p : e->allocs) cudaFree(p);
   if (e->pin) cudaFreeHost(e->pin);
   if (e->cudnn) cudnnDestroy(e->cudnn);
@@ -921,8 +974,18 @@ static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t
     PROF(e, "maskreg", img_bytes, 0, st, dp::launch_maskreg(a->mask, e->loss_density, e->group_lasso, e->win_dev, e->grp_ss, B, H, H, UNIT, st)); KERNEL_OK(); ++e->launches;
   }
   const float inv_s = 1.0f / (float)a->S_total;
-  for (int n0 = 0; n0 < N; n0 += e->chunk) {
+  // Two lanes: chunks alternate between two workspaces / internal streams (only when every chunk holds whole
+  // images, so no two chunks accumulate into the same G[b]).  Everything enqueued so far is on `st`.
+  cudaStream_t const user_st = st;
+  const bool dual = e->lanes.size() == 2 && N > e->chunk && (e->chunk % S == 0);
+  if (dual) {
+    CUDA_OK(cudaEventRecord(e->ev_prep, user_st));
+    for (auto& L : e->lanes) CUDA_OK(cudaStreamWaitEvent(L.stream, e->ev_prep, 0));
+  }
+  int chunk_id = 0;
+  for (int n0 = 0; n0 < N; n0 += e->chunk, ++chunk_id) {
     const int n = std::min(e->chunk, N - n0);
+    if (dual) { e->use_lane(chunk_id & 1); st = e->lanes[chunk_id & 1].stream; }
     if (xf_bytes) {
       PROF(e, "expand_affine", (double)n * H * H * 3 * e->es + 3.0 * H * H * 4 * (double)n / S, 0, st,
            dp::launch_expand_affine(e->adv_x, e->xf_d, rects, e->net_in, S, n0, n, H, H, e->Cp, e->bf16, st));
@@ -947,6 +1010,14 @@ static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t
            dp::launch_reduce(e->d_input, rects, a->grad_adv, B, S, n0, n, H, H, e->Cpd, e->bf16, st));
     }
     KERNEL_OK(); ++e->launches;
+  }
+  if (dual) {
+    for (auto& L : e->lanes) {
+      CUDA_OK(cudaEventRecord(L.done, L.stream));
+      CUDA_OK(cudaStreamWaitEvent(user_st, L.done, 0));
+    }
+    e->use_lane(0);
+    st = user_st;
   }
   // results -> host (pinned staging, one sync)
   unsigned char* out = e->pin + d2h_off;
