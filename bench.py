@@ -380,6 +380,7 @@ def run_native(args):
             kern[k] = d
         out["kernels"] = kern
         out["kernels_total_ms"] = round(tot, 3)
+        out["kernels_note"] = "one step profiled with CUDA events around every launch, chunks serialised on ONE lane; the timed steps overlap two lanes (two streams), so ms_per_step < kernels_total_ms"
         # ---- CPU baseline: oracle port on this box's host cores, bounded sample ----------------------------
         if world == 1 and not args.no_cpu_baseline:
             try:

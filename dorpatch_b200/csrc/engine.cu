@@ -977,7 +977,8 @@ static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t
   // Two lanes: chunks alternate between two workspaces / internal streams (only when every chunk holds whole
   // images, so no two chunks accumulate into the same G[b]).  Everything enqueued so far is on `st`.
   cudaStream_t const user_st = st;
-  const bool dual = e->lanes.size() == 2 && N > e->chunk && (e->chunk % S == 0);
+  // (the per-category profiler serialises on one lane so that category times do not overlap)
+  const bool dual = e->lanes.size() == 2 && N > e->chunk && (e->chunk % S == 0) && !e->prof_on;
   if (dual) {
     CUDA_OK(cudaEventRecord(e->ev_prep, user_st));
     for (auto& L : e->lanes) CUDA_OK(cudaStreamWaitEvent(L.stream, e->ev_prep, 0));
