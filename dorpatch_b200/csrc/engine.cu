@@ -632,6 +632,7 @@ struct dp_engine {
   // producing d_input (bf16 own-stem path; the per-sample input gradient is never materialised).
   struct FusedReduce { const int16_t* rects; float* G; int B, S, n0; };
   bool fused_stem_bwd = false;     // set at create: own_stem && DORPATCH_STEM_BWD != "cudnn"
+  bool fused_pool_bwd = false;     // ... && DORPATCH_POOL_BWD != "separate": max-pool backward fused in as well
   bool stem_bwd_fused_ok() const { return fused_stem_bwd; }
   void backward(int N, const float* dlog, cudaStream_t st, const FusedReduce* fused = nullptr) {
     CUDNN_OK(cudnnSetStream(cudnn, st));
@@ -672,6 +673,15 @@ struct dp_engine {
       std::swap(GA, GD);
     }
     const int hs = Hs();
+    if (fused != nullptr && fused_pool_bwd) {
+      // max-pool backward + stem dgrad + masked EOT reduce in one kernel: neither d_stem nor d_input is written
+      PROF(this, "stem_bwd_reduce", (double)N * (hs / 2) * (hs / 2) * STEM_CH * (es + 1) + 3.0 * H * H * 4 * (double)N / fused->S,
+           2.0 * N * hs * hs * STEM_CH * 147, st,
+           dp::launch_stem_bwd_pool_reduce(GA, pool_amax, stem.w, stem.cin_pad, fused->rects, fused->G, fused->B, fused->S, fused->n0, N, H, H, st));
+      KERNEL_OK(); ++launches;
+      d_input = nullptr;
+      return;
+    }
     PROF(this, "maxpool_bwd", (double)N * (hs * hs + (hs / 2) * (hs / 2)) * STEM_CH * es, 0, st,
          dp::launch_maxpool_backward(GA, pool_amax, GB, N, hs, hs, STEM_CH, bf16, st)); KERNEL_OK(); ++launches;
     if (fused != nullptr) {
@@ -754,6 +764,8 @@ int32_t dp_engine_create(const dp_config* cfg, dp_engine** out) {
     e->Cp = e->own_stem ? 3 : e->Cpd;
     const char* sb_env = getenv("DORPATCH_STEM_BWD");
     e->fused_stem_bwd = e->own_stem && !(sb_env && strcmp(sb_env, "cudnn") == 0);
+    const char* pb_env = getenv("DORPATCH_POOL_BWD");
+    e->fused_pool_bwd = e->fused_stem_bwd && !(pb_env && strcmp(pb_env, "separate") == 0);
     e->H = cfg->img; e->K = cfg->n_classes; e->chunk = cfg->chunk;
     e->cudnn_dt = e->bf16 ? CUDNN_DATA_BFLOAT16 : CUDNN_DATA_FLOAT;
     e->cuda_dt = e->bf16 ? CUDA_R_16BF : CUDA_R_32F;

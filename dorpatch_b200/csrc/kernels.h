@@ -51,6 +51,10 @@ void launch_stem_forward(const void* in, const void* w_kn, void* out, int N, int
 void launch_stem_bwd_reduce(const void* dY, const void* w_krsc, int cin_pad, const int16_t* rects, float* G, int B, int S,
                             int n0, int n, int H, int W, cudaStream_t st);
 
+// same, additionally fusing the pad+max-pool backward (reads d_pool + the saved argmax; d_stem never hits HBM)
+void launch_stem_bwd_pool_reduce(const void* dpool, const int8_t* amax, const void* w_krsc, int cin_pad, const int16_t* rects,
+                                 float* G, int B, int S, int n0, int n, int H, int W, cudaStream_t st);
+
 // ---- patch-side kernels (kernels_patch.cu) -------------------------------------------
 // utils.clip + add: adv_x = x + min(eps/||m(p-x)||,1) * m(p-x); l2[b], scale[b] dev outputs.
 void launch_paste(const float* x, const float* mask, const float* pattern, float* adv_x, float* l2, float* scale,

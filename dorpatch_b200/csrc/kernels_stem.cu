@@ -296,6 +296,193 @@ __global__ void __launch_bounds__(stemb::THREADS, 2) stem_bwd_reduce_kernel(cons
   }
 }
 
+// Variant that also fuses the backward of ConstantPad2d(1,0)+MaxPool(3,2): reads d_pool [n,Hp,Wp,64] + the int8
+// argmax saved by the forward pass and rebuilds each sample's d_stem patch in shared memory (fp32 sum of the <= 4
+// windows that selected a stem pixel, rounded once to bf16 -- bit-identical to maxpool_bwd_kernel's output), so the
+// [N,112,112,64] stem-output gradient is never written to HBM either.
+namespace stemb {
+constexpr int RR = 7, RC = 11;                                   // pooled-window region feeding one patch
+constexpr size_t REGION_BYTES = (size_t)RR * RC * (128 + 64);    // d_pool (bf16 x64) + argmax (int8 x64) per window
+constexpr size_t SMEM_POOL = W_BYTES + PATCH_BYTES + 2 * REGION_BYTES;
+}  // namespace stemb
+
+__global__ void __launch_bounds__(stemb::THREADS, 2) stem_bwd_pool_reduce_kernel(const __nv_bfloat16* __restrict__ dpool,
+                                                                                  const int8_t* __restrict__ amax,
+                                                                                  const __nv_bfloat16* __restrict__ w_krsc,
+                                                                                  int cin_pad, const int16_t* __restrict__ rects,
+                                                                                  float* __restrict__ G, int S, int n0, int n,
+                                                                                  int H, int W) {
+  using namespace stemb;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* Ws = smem_raw;
+  unsigned char* patch = smem_raw + W_BYTES;                      // [PR][PC][PIX]
+  unsigned char* region = patch + PATCH_BYTES;                    // [2][RR*RC][128 + 64]
+  const int Ho = H / 2, Wo = W / 2, Hp = H / 4, Wp = W / 4, Hc = H / 2, Wc = W / 2;
+  const int tiles_j = (Wc + TJ - 1) / TJ;
+  const int ti = blockIdx.x / tiles_j, tj = blockIdx.x % tiles_j;
+  const int b = n0 / S + blockIdx.y;
+  const int lo = max(n0, b * S), hi = min(n0 + n, (b + 1) * S);
+  if (lo >= hi) return;
+  const int i0 = ti * TI, j0 = tj * TJ;
+  const int wy0 = i0 / 2 - 1, wx0 = j0 / 2 - 1;                   // first pooled window row / col of the region
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int q = threadIdx.x; q < 49 * 64; q += THREADS) {
+    const int t = q >> 6, k = q & 63;
+    int cls = 0, tl = t;
+    if (tl >= 9) { cls = 1; tl -= 9; if (tl >= 12) { cls = 2; tl -= 12; if (tl >= 12) { cls = 3; tl -= 12; } } }
+    const int py = cls >> 1, px = cls & 1, nkx = px ? 4 : 3;
+    const int ky = (py ? 0 : 1) + 2 * (tl / nkx), kx = (px ? 0 : 1) + 2 * (tl % nkx);
+    const __nv_bfloat16* src = w_krsc + ((size_t)(k * 7 + ky) * 7 + kx) * cin_pad;
+    __nv_bfloat16 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = (c < 3) ? src[c] : __float2bfloat16(0.f);
+    *reinterpret_cast<uint4*>(Ws + (size_t)q * 16) = *reinterpret_cast<const uint4*>(v);
+  }
+
+  auto load_region = [&](int sample, int buf) {
+    const __nv_bfloat16* sp = dpool + (size_t)(sample - n0) * Hp * Wp * 64;
+    const int8_t* sa = amax + (size_t)(sample - n0) * Hp * Wp * 64;
+    unsigned char* dst = region + (size_t)buf * REGION_BYTES;
+    for (int q = threadIdx.x; q < RR * RC * 12; q += THREADS) {   // 8 chunks of d_pool + 4 chunks of argmax per window
+      const int win = q / 12, ch = q % 12;
+      const int wy = wy0 + win / RC, wx = wx0 + win % RC;
+      unsigned char* d = dst + (size_t)win * 192 + ch * 16;
+      if (wy >= 0 && wy < Hp && wx >= 0 && wx < Wp) {
+        const size_t o = ((size_t)wy * Wp + wx) * 64;
+        if (ch < 8) cp_async16(d, sp + o + ch * 8);
+        else cp_async16(d, sa + o + (ch - 8) * 16);
+      } else {
+        *reinterpret_cast<uint4*>(d) = ch < 8 ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      }
+    }
+    cp_commit();
+  };
+
+  float tot[4][4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { tot[c][0] = tot[c][1] = tot[c][2] = tot[c][3] = 0.f; }
+  const int g = lane >> 2, t4 = lane & 3;
+  const int irow = i0 + warp;
+
+  load_region(lo, 0);
+  for (int s = lo; s < hi; ++s) {
+    const int buf = (s - lo) & 1;
+    if (s + 1 < hi) { load_region(s + 1, buf ^ 1); cp_wait<1>(); } else { cp_wait<0>(); }
+    __syncthreads();
+    // ---- rebuild the d_stem patch of this sample from the pooled windows (max-pool backward) ----
+    const unsigned char* rg = region + (size_t)buf * REGION_BYTES;
+    for (int q = threadIdx.x; q < PR * PC * 8; q += THREADS) {
+      const int pix = q >> 3, ch = q & 7;
+      const int oy = i0 - 1 + pix / PC, ox = j0 - 1 + pix % PC;
+      float acc8[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc8[k] = 0.f;
+      if (oy >= 0 && oy < Ho && ox >= 0 && ox < Wo) {
+        for (int wy = oy / 2; wy <= (oy + 1) / 2; ++wy) {
+          const int ky = oy - 2 * wy + 1;
+          if (wy >= Hp || ky < 0 || ky > 2) continue;
+          for (int wx = ox / 2; wx <= (ox + 1) / 2; ++wx) {
+            const int kx = ox - 2 * wx + 1;
+            if (wx >= Wp || kx < 0 || kx > 2) continue;
+            const unsigned char* wp = rg + (size_t)((wy - wy0) * RC + (wx - wx0)) * 192;
+            const uint4 dv = *reinterpret_cast<const uint4*>(wp + ch * 16);
+            const uint2 av = *reinterpret_cast<const uint2*>(wp + 128 + ch * 8);
+            const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&dv);
+            const uint32_t am[2] = {av.x, av.y};
+            const int want = ky * 3 + kx;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if ((int)((am[k >> 2] >> (8 * (k & 3))) & 0xffu) == want) {
+                const float2 f = __bfloat1622float2(dh[k >> 1]);
+                acc8[k] += (k & 1) ? f.y : f.x;
+              }
+            }
+          }
+        }
+      }
+      __nv_bfloat162 o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = __floats2bfloat162_rn(acc8[2 * k], acc8[2 * k + 1]);
+      *reinterpret_cast<uint4*>(patch + (size_t)pix * PIX + ch * 16) = *reinterpret_cast<const uint4*>(o);
+    }
+    __syncthreads();
+    const unsigned char* pb = patch;
+    short r[16];
+    if (rects != nullptr) {
+      const int4* rp = reinterpret_cast<const int4*>(rects + (size_t)s * 16);
+      *reinterpret_cast<int4*>(r) = __ldg(rp);
+      *reinterpret_cast<int4*>(r + 8) = __ldg(rp + 1);
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; }
+#pragma unroll
+    for (int di = -1; di <= 2; ++di) {
+#pragma unroll
+      for (int dj = -1; dj <= 2; ++dj) {
+        const unsigned char* arow = pb + ((size_t)(warp + di + 1) * PC + (lane & 15) + dj + 1) * PIX + (lane >> 4) * 16;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t a0, a1, a2, a3;
+          stem::ldmatrix_x4(a0, a1, a2, a3, arow + kk * 32);
+#pragma unroll
+          for (int cls = 0; cls < 4; ++cls) {
+            const int py = cls >> 1, px = cls & 1, nkx = px ? 4 : 3;
+            if ((di == 2 && !py) || (dj == 2 && !px)) continue;
+            const int t = ((py ? 2 : 1) - di) * nkx + ((px ? 2 : 1) - dj);
+            const int tap0 = cls == 0 ? 0 : (cls == 1 ? 9 : (cls == 2 ? 21 : 33));
+            uint32_t b0, b1;
+            ldmatrix_x2_trans(b0, b1, Ws + ((size_t)(tap0 + t) * 64 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * 16);
+            stem::mma_bf16(acc[cls], a0, a1, a2, a3, b0, b1);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int cls = 0; cls < 4; ++cls) {
+      const int py = cls >> 1, px = cls & 1;
+      const int y = 2 * irow + py, xA = 2 * (j0 + g) + px, xB = 2 * (j0 + g + 8) + px;
+      const bool keepA = rects == nullptr || !rect_hit(r, y, xA);
+      const bool keepB = rects == nullptr || !rect_hit(r, y, xB);
+      if (keepA) { tot[cls][0] += acc[cls][0]; tot[cls][1] += acc[cls][1]; }
+      if (keepB) { tot[cls][2] += acc[cls][2]; tot[cls][3] += acc[cls][3]; }
+    }
+    __syncthreads();                                               // patch / region[buf] free for the next samples
+  }
+  const bool first = (lo == b * S);
+  if (irow < Hc && t4 < 2) {
+#pragma unroll
+    for (int cls = 0; cls < 4; ++cls) {
+      const int py = cls >> 1, px = cls & 1;
+      const int y = 2 * irow + py;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int x = 2 * (j0 + g + half * 8) + px;
+        if (x >= W) continue;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = 2 * t4 + e;
+          if (c >= 3) continue;
+          float* gp = G + ((size_t)b * 3 + c) * H * W + (size_t)y * W + x;
+          const float v = 2.0f * tot[cls][half * 2 + e];
+          *gp = first ? v : (*gp + v);
+        }
+      }
+    }
+  }
+}
+
+void launch_stem_bwd_pool_reduce(const void* dpool, const int8_t* amax, const void* w_krsc, int cin_pad, const int16_t* rects,
+                                 float* G, int B, int S, int n0, int n, int H, int W, cudaStream_t st) {
+  (void)B;
+  cudaFuncSetAttribute(stem_bwd_pool_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stemb::SMEM_POOL);
+  const int nb = (n0 + n - 1) / S - n0 / S + 1;
+  const int tiles = ((H / 2 + stemb::TI - 1) / stemb::TI) * ((W / 2 + stemb::TJ - 1) / stemb::TJ);
+  stem_bwd_pool_reduce_kernel<<<dim3(tiles, nb), stemb::THREADS, stemb::SMEM_POOL, st>>>(
+      (const __nv_bfloat16*)dpool, amax, (const __nv_bfloat16*)w_krsc, cin_pad, rects, G, S, n0, n, H, W);
+}
+
 void launch_stem_bwd_reduce(const void* dY, const void* w_krsc, int cin_pad, const int16_t* rects, float* G, int B, int S,
                             int n0, int n, int H, int W, cudaStream_t st) {
   (void)B;
