@@ -632,7 +632,7 @@ struct dp_engine {
   // producing d_input (bf16 own-stem path; the per-sample input gradient is never materialised).
   struct FusedReduce { const int16_t* rects; float* G; int B, S, n0; };
   bool fused_stem_bwd = false;     // set at create: own_stem && DORPATCH_STEM_BWD != "cudnn"
-  bool fused_pool_bwd = false;     // ... && DORPATCH_POOL_BWD != "separate": max-pool backward fused in as well
+  bool fused_pool_bwd = false;     // ... && DORPATCH_POOL_BWD == "fused": max-pool backward fused in as well (slower, off)
   bool stem_bwd_fused_ok() const { return fused_stem_bwd; }
   void backward(int N, const float* dlog, cudaStream_t st, const FusedReduce* fused = nullptr) {
     CUDNN_OK(cudnnSetStream(cudnn, st));
@@ -765,7 +765,9 @@ int32_t dp_engine_create(const dp_config* cfg, dp_engine** out) {
     const char* sb_env = getenv("DORPATCH_STEM_BWD");
     e->fused_stem_bwd = e->own_stem && !(sb_env && strcmp(sb_env, "cudnn") == 0);
     const char* pb_env = getenv("DORPATCH_POOL_BWD");
-    e->fused_pool_bwd = e->fused_stem_bwd && !(pb_env && strcmp(pb_env, "separate") == 0);
+    // measured: rebuilding the d_stem patch in shared memory costs more than the saved HBM round trip
+    // (2.25 ms vs 1.33 + 0.71 ms per 512-sample step) -> off unless DORPATCH_POOL_BWD=fused
+    e->fused_pool_bwd = e->fused_stem_bwd && (pb_env && strcmp(pb_env, "fused") == 0);
     e->H = cfg->img; e->K = cfg->n_classes; e->chunk = cfg->chunk;
     e->cudnn_dt = e->bf16 ? CUDNN_DATA_BFLOAT16 : CUDNN_DATA_FLOAT;
     e->cuda_dt = e->bf16 ? CUDA_R_16BF : CUDA_R_32F;
