@@ -454,9 +454,11 @@ namespace gnc {
 struct Pipe {
   uint64_t* bar;      // [2] mbarriers
   int nbuf;
+  static constexpr int CHUNK0 = 80;   // chunk barriers at byte 640 of the header; <= 7 chunks of a <= 220 KB slab
   __device__ __forceinline__ void init() {
     if (threadIdx.x == 0) {
       for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + i)));
+      for (int i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar + CHUNK0 + i)));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -486,6 +488,20 @@ struct Pipe {
           : "memory");
     }
   }
+  // One-shot chunked load (one cluster per sample): every 32 KB bulk copy completes on its own mbarrier
+  // (bar[CHUNK0 + k]), so the first pass over the slab starts on chunk 0 while the rest is in flight.
+  __device__ __forceinline__ void issue_chunked(void* dst, const void* src, uint32_t bytes) {   // thread 0, once, after init()
+    int k = 0;
+    for (uint32_t off = 0; off < bytes; off += BULK_CHUNK, ++k) {
+      const uint32_t nb = bytes - off < BULK_CHUNK ? bytes - off : BULK_CHUNK;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar + CHUNK0 + k)), "r"(nb) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32((const char*)dst + off)),
+                   "l"((const char*)src + off), "r"(nb), "r"(smem_u32(bar + CHUNK0 + k))
+                   : "memory");
+    }
+  }
+  __device__ __forceinline__ void wait_chunk(int k) { wait(CHUNK0 + k, 0u); }
 };
 }  // namespace gnc
 
@@ -500,6 +516,7 @@ __global__ void __launch_bounds__(gnc::MAX_THREADS) gn_fwd_cluster_kernel(const 
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+  const bool chunked = nbuf == 3;   // one cluster per sample, slab loaded once through per-chunk barriers
   gnc::Pipe pipe{reinterpret_cast<uint64_t*>(smem), nbuf};
   float* part = reinterpret_cast<float*>(smem + 64);          // [32][2] this CTA's partials
   float* s_mean = reinterpret_cast<float*>(smem + 64 + 256);  // [32]
@@ -519,19 +536,28 @@ __global__ void __launch_bounds__(gnc::MAX_THREADS) gn_fwd_cluster_kernel(const 
     const int b = nbuf == 2 ? (it & 1) : 0;
     const uint32_t parity = nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
     if (threadIdx.x == 0) {
-      if (it == 0 || nbuf == 1) pipe.issue(slabs + (size_t)b * slab_stride, x + ((size_t)n * P + p0) * C, slab_bytes, b);
-      if (nbuf == 2 && n + n_clusters < N)
-        pipe.issue(slabs + (size_t)(b ^ 1) * slab_stride, x + ((size_t)(n + n_clusters) * P + p0) * C, slab_bytes, b ^ 1);
+      if (chunked) pipe.issue_chunked(slabs, x + ((size_t)n * P + p0) * C, slab_bytes);
+      else {
+        if (it == 0 || nbuf != 2) pipe.issue(slabs + (size_t)b * slab_stride, x + ((size_t)n * P + p0) * C, slab_bytes, b);
+        if (nbuf == 2 && n + n_clusters < N)
+          pipe.issue(slabs + (size_t)(b ^ 1) * slab_stride, x + ((size_t)(n + n_clusters) * P + p0) * C, slab_bytes, b ^ 1);
+      }
     }
-    const uint32_t slab_a = gnc::smem_u32(slabs + (size_t)b * slab_stride) + (uint32_t)((trow * C + tcol * V) * sizeof(T));
+    const uint32_t toff = (uint32_t)((trow * C + tcol * V) * sizeof(T));
+    const uint32_t slab_a = gnc::smem_u32(slabs + (size_t)b * slab_stride) + toff;
     const uint32_t srow = (uint32_t)(rpi * C * sizeof(T));
-    pipe.wait(b, parity);
+    if (!chunked) pipe.wait(b, parity);
 
     float a[V], bq[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) { a[i] = 0.f; bq[i] = 0.f; }
     uint32_t sp = slab_a;
+    int have = -1;                                 // last slab chunk this thread has waited for
     for (int r = trow; r < rows; r += rpi, sp += srow) {
+      if (chunked) {
+        const int k = (int)((sp - slab_a + toff) / gnc::BULK_CHUNK);
+        if (k != have) { pipe.wait_chunk(k); have = k; }
+      }
       Vec<T> v; v.load_shared(sp);
       float f[V]; v.unpack(f);
 #pragma unroll
@@ -600,6 +626,7 @@ __global__ void __launch_bounds__(gnc::MAX_THREADS, 1) gn_bwd_cluster_kernel(con
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+  const bool chunked = nbuf == 3;   // one cluster per sample, x slab loaded once through per-chunk barriers
   gnc::Pipe pipe{reinterpret_cast<uint64_t*>(smem), nbuf};
   float* part = reinterpret_cast<float*>(smem + 64);
   float* s_1 = reinterpret_cast<float*>(smem + 64 + 256);
@@ -623,9 +650,12 @@ __global__ void __launch_bounds__(gnc::MAX_THREADS, 1) gn_bwd_cluster_kernel(con
     const uint32_t parity = nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
     const size_t base = ((size_t)n * P + p0) * C;
     if (threadIdx.x == 0) {
-      if (it == 0 || nbuf == 1) pipe.issue(slabs + (size_t)b * slab_stride, x + base, slab_bytes, b);
-      if (nbuf == 2 && n + n_clusters < N)
-        pipe.issue(slabs + (size_t)(b ^ 1) * slab_stride, x + ((size_t)(n + n_clusters) * P + p0) * C, slab_bytes, b ^ 1);
+      if (chunked) pipe.issue_chunked(slabs, x + base, slab_bytes);
+      else {
+        if (it == 0 || nbuf != 2) pipe.issue(slabs + (size_t)b * slab_stride, x + base, slab_bytes, b);
+        if (nbuf == 2 && n + n_clusters < N)
+          pipe.issue(slabs + (size_t)(b ^ 1) * slab_stride, x + ((size_t)(n + n_clusters) * P + p0) * C, slab_bytes, b ^ 1);
+      }
     }
     const uint32_t slab_a = gnc::smem_u32(slabs + (size_t)b * slab_stride) + (uint32_t)(tcol * V * sizeof(T));
     const uint32_t crow = (uint32_t)(C * sizeof(T));
@@ -641,10 +671,11 @@ __global__ void __launch_bounds__(gnc::MAX_THREADS, 1) gn_bwd_cluster_kernel(con
       sa[i] = rs[UG ? 0 : i] * ga[i];
       sb[i] = beta[tcol * V + i] - mu[UG ? 0 : i] * sa[i];
     }
-    pipe.wait(b, parity);
+    if (!chunked) pipe.wait(b, parity);
     float a[V], bq[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) { a[i] = 0.f; bq[i] = 0.f; }
+    int have = -1;                                 // last slab chunk this thread has waited for
     for (int r0 = trow; r0 < rows; r0 += rpi * U) {
       Vec<T> vd[U];
 #pragma unroll
@@ -656,6 +687,10 @@ __global__ void __launch_bounds__(gnc::MAX_THREADS, 1) gn_bwd_cluster_kernel(con
       for (int u = 0; u < U; ++u) {
         const int r = r0 + u * rpi;
         if (r < rows) {
+          if (chunked) {
+            const int k = (int)(((uint32_t)r * crow + (uint32_t)(tcol * V * sizeof(T))) / gnc::BULK_CHUNK);
+            if (k != have) { pipe.wait_chunk(k); have = k; }
+          }
           Vec<T> vx; vx.load_shared(slab_a + (uint32_t)r * crow);
           float fx[V], fd[V]; vx.unpack(fx); vd[u].unpack(fd);
 #pragma unroll
@@ -874,6 +909,13 @@ static bool gn_plan(int P, int C, size_t es, GnPlan* out) {
     }
   }
   return false;
+}
+// DORPATCH_GN_CHUNKED (default 1; 0 = one barrier for the whole slab): one-cluster-per-sample launches load the slab through per-32KB mbarriers
+// (kernel argument nbuf = 3) so the statistics pass overlaps the tail of the TMA load.
+static int gn_nbuf(const GnPlan& pl) {
+  static int chunked = -1;
+  if (chunked < 0) { const char* e = getenv("DORPATCH_GN_CHUNKED"); chunked = e ? atoi(e) : 1; }
+  return (!pl.persistent && chunked) ? 3 : pl.nbuf;
 }
 static int g_num_sms = 0;
 static int gn_grid(const GnPlan& pl, int N) {
@@ -1149,8 +1191,8 @@ void launch_gn_relu_forward(const void* x, void* y, const float* gamma, const fl
   if (gn_plan(P, C, bf16 ? 2 : 4, &pl)) {
     const int grid = gn_grid(pl, N);
     bool ok;
-    if (bf16) ok = launch_cluster(gn_fwd_cluster_kernel<__nv_bfloat16>, pl.cl, grid, pl.threads, pl.smem, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, stats, N, P, C, pl.nbuf, pl.slab_stride);
-    else ok = launch_cluster(gn_fwd_cluster_kernel<float>, pl.cl, grid, pl.threads, pl.smem, st, (const float*)x, (float*)y, gamma, beta, stats, N, P, C, pl.nbuf, pl.slab_stride);
+    if (bf16) ok = launch_cluster(gn_fwd_cluster_kernel<__nv_bfloat16>, pl.cl, grid, pl.threads, pl.smem, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, stats, N, P, C, gn_nbuf(pl), pl.slab_stride);
+    else ok = launch_cluster(gn_fwd_cluster_kernel<float>, pl.cl, grid, pl.threads, pl.smem, st, (const float*)x, (float*)y, gamma, beta, stats, N, P, C, gn_nbuf(pl), pl.slab_stride);
     if (ok) return;
     cudaGetLastError();   // clear and fall back
   }
@@ -1186,7 +1228,7 @@ void launch_gn_relu_backward(const void* dy, const void* x, const void* addend, 
   if (gn_plan(P, C, bf16 ? 2 : 4, &pl)) {
     const int grid = gn_grid(pl, N);
     bool ok;
-#define GNB(TT, UGV) launch_cluster(gn_bwd_cluster_kernel<TT, UGV>, pl.cl, grid, pl.threads, pl.smem, st, (const TT*)dy, (const TT*)x, (const TT*)addend, (TT*)dx, gamma, beta, stats, N, P, C, pl.nbuf, pl.slab_stride)
+#define GNB(TT, UGV) launch_cluster(gn_bwd_cluster_kernel<TT, UGV>, pl.cl, grid, pl.threads, pl.smem, st, (const TT*)dy, (const TT*)x, (const TT*)addend, (TT*)dx, gamma, beta, stats, N, P, C, gn_nbuf(pl), pl.slab_stride)
     if (bf16) ok = ug ? GNB(__nv_bfloat16, true) : GNB(__nv_bfloat16, false);
     else ok = ug ? GNB(float, true) : GNB(float, false);
 #undef GNB

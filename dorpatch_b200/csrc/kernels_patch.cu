@@ -304,11 +304,32 @@ static void expand_launch(const ExpandParams& p, int num_sms, cudaStream_t st) {
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   if (ctas_per_sm > 6) ctas_per_sm = 6;
   const int target = num_sms * ctas_per_sm;
-  int sg = 1;
-  while (nb * tiles * sg < target && sg * EXP_WARPS < p.S && sg < 32) sg *= 2;
+  // Work split: items = images x row tiles x sample groups, walked grid-stride.  Every CTA should get
+  // the same number of items (a 1.2-wave launch costs two full waves), so the grid is items / waves
+  // rounded up, and the sample-group count is the one whose balanced grid fills most of the machine
+  // while a group still holds at least one sample per warp.
+  static int sg_env = -1, balance = 1;
+  if (sg_env < 0) {
+    const char* e = getenv("DORPATCH_K1_SG"); sg_env = e ? atoi(e) : 0;
+    if (const char* b = getenv("DORPATCH_K1_BALANCE")) balance = atoi(b);
+  }
+  int sg = 1, grid = 1;
+  if (!balance) {                                   // previous policy: fill the machine, ragged last wave
+    while (nb * tiles * sg < target && sg * EXP_WARPS < p.S && sg < 32) sg *= 2;
+    grid = nb * tiles * sg;
+    if (grid > target) grid = target;
+  } else {
+    int best_grid = 0;
+    for (int c = 1; c <= 32 && (c == 1 || c * EXP_WARPS <= p.S); c *= 2) {
+      if (sg_env > 0 && c != sg_env) continue;
+      const int items = nb * tiles * c;
+      const int waves = (items + target - 1) / target;
+      const int g = (items + waves - 1) / waves;
+      if (g > best_grid + best_grid / 16) { best_grid = g; sg = c; grid = g; }   // prefer fewer groups unless >6 % more CTAs
+    }
+    if (best_grid == 0) { sg = 1; const int items = nb * tiles; const int waves = (items + target - 1) / target; grid = (items + waves - 1) / waves; }
+  }
   q.sgroups = sg;
-  int grid = nb * tiles * sg;
-  if (grid > target) grid = target;
   expand_kernel<T, CP, FUSED><<<grid, EXP_THREADS, smem, st>>>(q);
 }
 
