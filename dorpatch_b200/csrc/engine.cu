@@ -933,8 +933,17 @@ int32_t dp_predict(dp_engine* e, const float* img, int32_t B, int32_t S, const i
   const int N = B * S;
   if (N < 1) fail("dp_predict: empty batch");
   e->h2d_samples(rects_host, N, st);
-  for (int n0 = 0; n0 < N; n0 += e->chunk) {
+  // forward-only scan (collect_failure, PatchCleanser): chunks alternate between the two lanes like dp_attack_grad
+  cudaStream_t const user_st = st;
+  const bool dual = e->lanes.size() == 2 && N > e->chunk && !e->prof_on;
+  if (dual) {
+    CUDA_OK(cudaEventRecord(e->ev_prep, user_st));
+    for (auto& L : e->lanes) CUDA_OK(cudaStreamWaitEvent(L.stream, e->ev_prep, 0));
+  }
+  int chunk_id = 0;
+  for (int n0 = 0; n0 < N; n0 += e->chunk, ++chunk_id) {
     const int n = std::min(e->chunk, N - n0);
+    if (dual) { e->use_lane(chunk_id & 1); st = e->lanes[chunk_id & 1].stream; }
     PROF(e, "expand_k1", (double)n * e->H * e->H * 3 * e->es + 3.0 * e->H * e->H * 4 * (double)n / S, 0, st,
          dp::launch_expand(img, nullptr, nullptr, nullptr, nullptr, rects_host ? e->rects_d : nullptr, e->net_in, B, S, n0, n,
                            e->H, e->H, e->Cp, e->bf16, false, e->num_sms, st));
@@ -942,6 +951,14 @@ int32_t dp_predict(dp_engine* e, const float* img, int32_t B, int32_t S, const i
     e->forward(n, e->net_in, false, st);
     dp::launch_argmax(e->logits, e->preds_d + n0, n, e->K, st); KERNEL_OK(); ++e->launches;
     if (logits_host) CUDA_OK(cudaMemcpyAsync(logits_host + (size_t)n0 * e->K, e->logits, (size_t)n * e->K * 4, cudaMemcpyDeviceToHost, st));
+  }
+  if (dual) {
+    for (auto& L : e->lanes) {
+      CUDA_OK(cudaEventRecord(L.done, L.stream));
+      CUDA_OK(cudaStreamWaitEvent(user_st, L.done, 0));
+    }
+    e->use_lane(0);
+    st = user_st;
   }
   CUDA_OK(cudaMemcpyAsync(preds_host, e->preds_d, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
