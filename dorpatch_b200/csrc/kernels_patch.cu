@@ -106,8 +106,8 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 constexpr int EXP_R_DEFAULT = 8;  // image rows per tile (DORPATCH_K1_ROWS overrides; must divide H)
 constexpr int EXP_THREADS = 256;
 constexpr int EXP_WARPS = EXP_THREADS / 32;
-constexpr int EXP_HDR = 512 + 4096;   // mbarrier + per-item rectangle cache (128 samples x 32 B)
-constexpr int EXP_RCACHE = 128;
+constexpr int EXP_HDR = 512 + 2048;   // mbarrier + per-item rectangle cache (64 samples x 32 B)
+constexpr int EXP_RCACHE = 64;
 
 __device__ __forceinline__ bool rect_hit(const short* r, int row, int col) {
 #pragma unroll
@@ -229,56 +229,65 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
         if (lane == 0) { ptx::bulk_store(dst, clean_b, out_bytes); ptx::bulk_commit(); }
         continue;
       }
-      // per-sample, row-independent classification of this lane's chunks (ch = lane + 32*j) against
-      // each rectangle's element interval: bit j of in_k = chunk fully inside, of pa_k = straddles an edge
-      uint32_t in_k[4], pa_k[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t bi = 0u, bp = 0u;
-        for (int j = 0, ch = lane; ch < row_chunks; ++j, ch += 32) {
-          const int e0 = ch * EPC;
-          const bool inside = e0 >= el[k] && e0 + EPC <= eh[k];
-          const bool part = !inside && e0 < eh[k] && e0 + EPC > el[k];
-          bi |= (inside ? 1u : 0u) << j;
-          bp |= (part ? 1u : 0u) << j;
-        }
-        in_k[k] = bi; pa_k[k] = bp;
-      }
-      for (int rr = 0; rr < EXP_R; ++rr) {
-        const int row = r0 + rr;
-        uint32_t zero_bits = 0u, part_bits = 0u;
-        bool rany = false;
+      // Row-independent part, once per sample: field j (EPC bits) of zm[k] = which elements of this lane's chunk
+      // (cb + lane + 32 j) rectangle k zeroes -- all ones inside, zero outside, a bit range on the <= 2 chunks that
+      // straddle an edge.  A row then only ORs the words of the rectangles that cover it.
+      constexpr int JB = 32 / EPC;                              // chunks per lane per mask word (4 bf16 / 8 fp32)
+      constexpr uint32_t FULL = (1u << EPC) - 1u;
+      for (int cb = 0; cb < row_chunks; cb += 32 * JB) {        // one pass for rows up to 2048 B (bf16) / 4096 B (fp32)
+        uint32_t zm[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const bool cov = row >= rr0[k] && row < rr1[k];
-          rany = rany || cov;
-          zero_bits |= cov ? in_k[k] : 0u;
-          part_bits |= cov ? pa_k[k] : 0u;
-        }
-        if (!rany) {                                            // clean row: bulk store
-          if (lane == 0) { ptx::bulk_store(dst + (size_t)rr * row_bytes, clean_b + (size_t)rr * row_bytes, row_bytes); ptx::bulk_commit(); }
-          continue;
-        }
-        part_bits &= ~zero_bits;
-        const uint4* crow = reinterpret_cast<const uint4*>(clean_b + (size_t)rr * row_bytes);
-        uint4* drow = reinterpret_cast<uint4*>(dst + (size_t)rr * row_bytes);
-        for (int j = 0, ch = lane; ch < row_chunks; ++j, ch += 32) {
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (!((zero_bits >> j) & 1u)) {
-            v = crow[ch];
-            if ((part_bits >> j) & 1u) {                        // <= 2 chunks per rectangle edge
-              T* ev = reinterpret_cast<T*>(&v);
-              const int e0 = ch * EPC;
+          uint32_t z = 0u;
 #pragma unroll
-              for (int q = 0; q < EPC; ++q) {
-                bool z = false;
+          for (int j = 0; j < JB; ++j) {
+            const int e0 = (cb + lane + 32 * j) * EPC;
+            const int lo = min(max(el[k] - e0, 0), EPC), hi = min(max(eh[k] - e0, 0), EPC);
+            const uint32_t m = hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+            z |= m << (EPC * j);
+          }
+          zm[k] = z;
+        }
+        for (int rr = 0; rr < EXP_R; ++rr) {
+          const int row = r0 + rr;
+          uint32_t Z = 0u;
+          bool rany = false;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) z = z || (row >= rr0[k] && row < rr1[k] && e0 + q >= el[k] && e0 + q < eh[k]);
-                if (z) ev[q] = from_float<T>(0.f);
+          for (int k = 0; k < 4; ++k) {
+            const bool cov = row >= rr0[k] && row < rr1[k];
+            rany = rany || cov;
+            Z |= cov ? zm[k] : 0u;
+          }
+          if (!rany) {                                          // clean row: bulk store
+            if (cb == 0 && lane == 0) { ptx::bulk_store(dst + (size_t)rr * row_bytes, clean_b + (size_t)rr * row_bytes, row_bytes); ptx::bulk_commit(); }
+            continue;
+          }
+          const uint4* crow = reinterpret_cast<const uint4*>(clean_b + (size_t)rr * row_bytes);
+          uint4* drow = reinterpret_cast<uint4*>(dst + (size_t)rr * row_bytes);
+#pragma unroll
+          for (int j = 0; j < JB; ++j) {
+            const int ch = cb + lane + 32 * j;
+            if (ch >= row_chunks) break;
+            const uint32_t m = (Z >> (EPC * j)) & FULL;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (m != FULL) {
+              v = crow[ch];
+              if (m != 0u) {                                    // edge chunk: clear the covered elements
+                if (EPC == 8) {                                 // two 16-bit elements per word
+                  v.x &= ~(((m & 1u) ? 0xffffu : 0u) | ((m & 2u) ? 0xffff0000u : 0u));
+                  v.y &= ~(((m & 4u) ? 0xffffu : 0u) | ((m & 8u) ? 0xffff0000u : 0u));
+                  v.z &= ~(((m & 16u) ? 0xffffu : 0u) | ((m & 32u) ? 0xffff0000u : 0u));
+                  v.w &= ~(((m & 64u) ? 0xffffu : 0u) | ((m & 128u) ? 0xffff0000u : 0u));
+                } else {
+                  if (m & 1u) v.x = 0u;
+                  if (m & 2u) v.y = 0u;
+                  if (m & 4u) v.z = 0u;
+                  if (m & 8u) v.w = 0u;
+                }
               }
             }
+            drow[ch] = v;
           }
-          drow[ch] = v;
         }
       }
     }
@@ -300,21 +309,24 @@ static void expand_launch(const ExpandParams& p, int num_sms, cudaStream_t st) {
   q.R = EXP_R;
   const int nb = (p.n0 + p.n - 1) / p.S - p.n0 / p.S + 1;
   const int tiles = p.H / EXP_R;
+  static int ctas_env = -1;
+  if (ctas_env < 0) { const char* e = getenv("DORPATCH_K1_CTAS"); ctas_env = e ? atoi(e) : 0; }
   int ctas_per_sm = (int)((200 * 1024) / smem);
+  if (ctas_env > 0) ctas_per_sm = ctas_env;                 // experiment knob: resident CTAs per SM assumed by the grid
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   if (ctas_per_sm > 6) ctas_per_sm = 6;
   const int target = num_sms * ctas_per_sm;
-  // Work split: items = images x row tiles x sample groups, walked grid-stride.  Every CTA should get
-  // the same number of items (a 1.2-wave launch costs two full waves), so the grid is items / waves
-  // rounded up, and the sample-group count is the one whose balanced grid fills most of the machine
-  // while a group still holds at least one sample per warp.
-  static int sg_env = -1, balance = 1;
+  // Work split: items = images x row tiles x sample groups, walked grid-stride by as many CTAs as are resident.
+  // DORPATCH_K1_BALANCE=1 instead sizes the grid to items / waves so that every CTA gets the same item count
+  // (measured on B200 at 32 x 16 samples: 0.060-0.070 ms against 0.056 ms -- fewer resident CTAs cost more than
+  // the ragged last wave), DORPATCH_K1_SG forces the sample-group count under that policy.
+  static int sg_env = -1, balance = 0;
   if (sg_env < 0) {
     const char* e = getenv("DORPATCH_K1_SG"); sg_env = e ? atoi(e) : 0;
     if (const char* b = getenv("DORPATCH_K1_BALANCE")) balance = atoi(b);
   }
   int sg = 1, grid = 1;
-  if (!balance) {                                   // previous policy: fill the machine, ragged last wave
+  if (!balance) {                                   // fill the machine, ragged last wave
     while (nb * tiles * sg < target && sg * EXP_WARPS < p.S && sg < 32) sg *= 2;
     grid = nb * tiles * sg;
     if (grid > target) grid = target;
