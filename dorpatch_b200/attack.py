@@ -15,7 +15,8 @@ Semantics beyond the reference:
   * the two ``set_target(preds_adv)`` call sites with a missing argument (attack.py:155,359,
     a TypeError in the reference) pass the label.
   * EOT sharding: with torch.distributed initialised, each rank evaluates S/world samples and
-    the ranks all-reduce the patch gradient once per step.
+    the ranks all-reduce the patch gradient once per step; the periodic universe scan
+    (collect_failure) is split over the ranks by mask index and its fail bits all-gathered.
 """
 import os
 
@@ -169,6 +170,31 @@ def exchange_shards(dist, G, loss_adv, preds):
     return loss_all, preds_all
 
 
+def scan_failures(predict, all_rects, y, targeted, dist=None, device="cpu"):
+    """collect_failure for one image (attack.py:384-406): indices of the universe masks under
+    which the attack fails.  `predict(rects[k,4,4]) -> labels[k]`.  With torch.distributed the
+    universe is split into contiguous shards, one per rank (the scan is
+    embarrassingly parallel over the mask index), and the fail bits are all-gathered, so every
+    rank returns the identical list and takes the identical bookkeeping decisions."""
+    n = all_rects.shape[0]
+    if dist is None:
+        f = np.asarray(predict(all_rects)) == y
+    else:
+        rank, world = dist.get_rank(), dist.get_world_size()
+        per = -(-n // world)
+        lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+        bits = torch.zeros(per, dtype=torch.uint8)
+        if hi > lo:
+            bits[:hi - lo] = torch.from_numpy((np.asarray(predict(all_rects[lo:hi])) == y).astype(np.uint8))
+        bits = bits.to(device)
+        outs = [torch.empty_like(bits) for _ in range(world)]
+        dist.all_gather(outs, bits)
+        f = torch.cat(outs).cpu().numpy()[:n].astype(bool)
+    if targeted:
+        f = ~f
+    return np.nonzero(f)[0].tolist()
+
+
 class DorPatch(object):
     def __init__(self):
         self.last_stats = {}
@@ -234,11 +260,8 @@ class DorPatch(object):
         steps = 0
 
         def scan(b, adv_x):                                      # collect_failure, attack.py:384-406
-            preds = eng.predict(adv_x[b:b + 1], n_mask, all_rects)
-            f = preds == st[b].y
-            if st[b].targeted:
-                f = ~f
-            failed = np.nonzero(f)[0].tolist()
+            failed = scan_failures(lambda r: eng.predict(adv_x[b:b + 1], r.shape[0], r), all_rects, st[b].y,
+                                   st[b].targeted, dist, dev)
             print(">> %d failures collected!" % len(failed))
             return failed
 

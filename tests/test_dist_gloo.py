@@ -48,3 +48,44 @@ def test_exchange_shards_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _scan_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dorpatch_b200.attack import scan_failures
+    ok = True
+    for n, y, targeted in ((2520, 3, False), (145, 1, True), (1, 0, False)):   # even split, ragged last shard, empty shard
+        rects = np.zeros((n, 4, 4), np.int16)
+        rects[:, 0, 0] = np.arange(n)                                     # tag every universe entry with its index
+        labels = np.random.RandomState(n).randint(0, 5, n)
+        seen = []
+
+        def predict(r):
+            seen.append(r[:, 0, 0].copy())
+            return labels[r[:, 0, 0]]
+
+        want = scan_failures(lambda r: labels[r[:, 0, 0]], rects, y, targeted)
+        got = scan_failures(predict, rects, y, targeted, dist, "cpu")
+        per = -(-n // world)
+        mine = np.arange(min(rank * per, n), min((rank + 1) * per, n))
+        ok = ok and got == want and (np.array_equal(np.concatenate(seen), mine) if len(mine) else not seen)
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_universe_scan_is_sharded_by_mask_index_world2():
+    """collect_failure under torch.distributed: every rank scans only its contiguous shard of the mask
+    universe and all ranks end with the single-process failure list."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_scan_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
