@@ -260,8 +260,15 @@ class DorPatch(object):
         steps = 0
 
         def scan(b, adv_x):                                      # collect_failure, attack.py:384-406
-            failed = scan_failures(lambda r: eng.predict(adv_x[b:b + 1], r.shape[0], r), all_rects, st[b].y,
-                                   st[b].targeted, dist, dev)
+            if dist is None:
+                preds = eng.predict(adv_x[b:b + 1], n_mask, all_rects)
+                f = preds == st[b].y
+                if st[b].targeted:
+                    f = ~f
+                failed = np.nonzero(f)[0].tolist()
+            else:                                                # universe split over the ranks by mask index
+                failed = scan_failures(lambda r: eng.predict(adv_x[b:b + 1], r.shape[0], r), all_rects, st[b].y,
+                                       st[b].targeted, dist, dev)
             print(">> %d failures collected!" % len(failed))
             return failed
 
