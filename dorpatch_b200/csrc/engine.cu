@@ -81,6 +81,7 @@ struct Block {
   // saved tensors / stats for backward (device, per chunk)
   void* h1 = nullptr; void* h2 = nullptr; void* out = nullptr;
   float* st1 = nullptr; float* st2 = nullptr; float* st3 = nullptr;
+  void* c1p = nullptr; void* c3p = nullptr;   // conv1 / conv3 weights as tcgen05 operand tiles (DORPATCH_FUSED_GEMM=1)
 };
 
 struct CudnnPlan {
@@ -105,6 +106,7 @@ struct dp_engine {
   int Cp = 4;               // channels per pixel of the network INPUT (3 = tight, own stem kernel)
   int Cpd = 4;              // channels per pixel of d(input) produced by the library dgrad (4 fp32 / 8 bf16)
   bool own_stem = false;    // bf16: hand-written tensor-core stem forward on the tight C=3 layout
+  bool fused_gemm = false;  // opt-in (DORPATCH_FUSED_GEMM=1, bf16): GN+ReLU applied inside the tcgen05 1x1-conv GEMM of kernels_gemm.cu
   void* stem_w_kn = nullptr;
   int H = 224, K = 1000, chunk = 64;
   int num_sms = 148;
@@ -308,6 +310,10 @@ struct dp_engine {
       make_conv(b.c1, b.cin, b.mid, 1, 1, 0, b.cin);
       make_conv(b.c2, b.mid, b.mid, 3, b.stride, 1, b.mid);
       make_conv(b.c3, b.mid, b.cout, 1, 1, 0, b.mid);
+      if (fused_gemm) {
+        b.c1p = dmalloc((size_t)b.mid * b.cin * 2);
+        b.c3p = dmalloc((size_t)b.cout * b.mid * 2);
+      }
     }
     make_gn(head_gn, WIDTHS[3]);
     fc_w = (float*)dmalloc((size_t)K * WIDTHS[3] * 4);
@@ -401,6 +407,11 @@ struct dp_engine {
         i = get(P("conv1.weight")); upload_conv(b.c1, ptrs[i], numels[i], st, tmp);
         i = get(P("conv2.weight")); upload_conv(b.c2, ptrs[i], numels[i], st, tmp);
         i = get(P("conv3.weight")); upload_conv(b.c3, ptrs[i], numels[i], st, tmp);
+        if (fused_gemm) {
+          dp::launch_gn_gemm_pack(b.c1.w, b.c1p, b.mid, b.cin, st); KERNEL_OK();
+          dp::launch_gn_gemm_pack(b.c3.w, b.c3p, b.cout, b.mid, st); KERNEL_OK();
+          CUDA_OK(cudaStreamSynchronize(st));
+        }
         i = get(P("norm1.weight")); upload_vec(b.n1.gamma, ptrs[i], numels[i], b.cin);
         i = get(P("norm1.bias")); upload_vec(b.n1.beta, ptrs[i], numels[i], b.cin);
         i = get(P("norm2.weight")); upload_vec(b.n2.gamma, ptrs[i], numels[i], b.mid);
@@ -594,9 +605,18 @@ struct dp_engine {
     int lid = 1;
     for (auto& b : blocks) {
       const int pin_ = b.hin * b.hin, pout = b.hout * b.hout;
+      // opt-in: statistics pass + tcgen05 GEMM that normalises its A operand on the way into shared memory
+      // (the relu(gn(.)) tensors of norm1 / norm3 are never written); blocks with a downsample branch keep norm1.
+      const bool fuse1 = fused_gemm && !b.has_ds && dp::gn_gemm_supported(pin_, b.cin, b.mid);
+      const bool fuse3 = fused_gemm && dp::gn_gemm_supported(pout, b.mid, b.cout);
       // xp = relu(gn1(cur))
-      PROF(this, "gn_relu_fwd", 2.0 * N * pin_ * b.cin * es, 0, st,
-           dp::launch_gn_relu_forward(cur, act, b.n1.gamma, b.n1.beta, gn_partial, b.st1, N, pin_, b.cin, bf16, st)); KERNEL_OK(); launches += 2;
+      if (fuse1) {
+        PROF(this, "gn_stats", 1.0 * N * pin_ * b.cin * es, 0, st, dp::launch_gn_stats(cur, gn_partial, b.st1, N, pin_, b.cin, bf16, st));
+        KERNEL_OK(); launches += 2;
+      } else {
+        PROF(this, "gn_relu_fwd", 2.0 * N * pin_ * b.cin * es, 0, st,
+             dp::launch_gn_relu_forward(cur, act, b.n1.gamma, b.n1.beta, gn_partial, b.st1, N, pin_, b.cin, bf16, st)); KERNEL_OK(); launches += 2;
+      }
       const void* shortcut = cur;
       if (b.has_ds) {
         const void* src = act;
@@ -607,13 +627,27 @@ struct dp_engine {
         gemm(N * pout, b.cout, b.cin, 0, b.ds.w, src, nullptr, 0.f, b.out, st);
         shortcut = b.out;
       }
-      gemm(N * pin_, b.mid, b.cin, 0, b.c1.w, act, nullptr, 0.f, b.h1, st);
+      if (fuse1) {
+        PROF(this, "gn_gemm1x1_fwd", ((double)N * pin_ * (b.cin + b.mid) + (double)b.mid * b.cin) * es, 2.0 * N * pin_ * b.mid * b.cin, st,
+             dp::launch_gn_gemm_forward(cur, b.c1p, b.st1, b.n1.gamma, b.n1.beta, nullptr, b.h1, N, pin_, b.cin, b.mid, st));
+        KERNEL_OK(); ++launches;
+      } else {
+        gemm(N * pin_, b.mid, b.cin, 0, b.c1.w, act, nullptr, 0.f, b.h1, st);
+      }
       PROF(this, "gn_relu_fwd", 2.0 * N * pin_ * b.mid * es, 0, st,
            dp::launch_gn_relu_forward(b.h1, act, b.n2.gamma, b.n2.beta, gn_partial, b.st2, N, pin_, b.mid, bf16, st)); KERNEL_OK(); launches += 2;
       conv_fwd(lid, b.c2, N, b.hin, b.hout, act, b.h2, st);
-      PROF(this, "gn_relu_fwd", 2.0 * N * pout * b.mid * es, 0, st,
-           dp::launch_gn_relu_forward(b.h2, act, b.n3.gamma, b.n3.beta, gn_partial, b.st3, N, pout, b.mid, bf16, st)); KERNEL_OK(); launches += 2;
-      gemm(N * pout, b.cout, b.mid, 0, b.c3.w, act, shortcut, 1.f, b.out, st);   // + shortcut fused as C operand
+      if (fuse3) {
+        PROF(this, "gn_stats", 1.0 * N * pout * b.mid * es, 0, st, dp::launch_gn_stats(b.h2, gn_partial, b.st3, N, pout, b.mid, bf16, st));
+        KERNEL_OK(); launches += 2;
+        PROF(this, "gn_gemm1x1_fwd", ((double)N * pout * (b.mid + 2.0 * b.cout) + (double)b.cout * b.mid) * es, 2.0 * N * pout * b.cout * b.mid, st,
+             dp::launch_gn_gemm_forward(b.h2, b.c3p, b.st3, b.n3.gamma, b.n3.beta, shortcut, b.out, N, pout, b.mid, b.cout, st));
+        KERNEL_OK(); ++launches;
+      } else {
+        PROF(this, "gn_relu_fwd", 2.0 * N * pout * b.mid * es, 0, st,
+             dp::launch_gn_relu_forward(b.h2, act, b.n3.gamma, b.n3.beta, gn_partial, b.st3, N, pout, b.mid, bf16, st)); KERNEL_OK(); launches += 2;
+        gemm(N * pout, b.cout, b.mid, 0, b.c3.w, act, shortcut, 1.f, b.out, st);   // + shortcut fused as C operand
+      }
       cur = b.out;
       ++lid;
     }
@@ -764,6 +798,8 @@ int32_t dp_engine_create(const dp_config* cfg, dp_engine** out) {
     e->Cp = e->own_stem ? 3 : e->Cpd;
     const char* sb_env = getenv("DORPATCH_STEM_BWD");
     e->fused_stem_bwd = e->own_stem && !(sb_env && strcmp(sb_env, "cudnn") == 0);
+    const char* fg_env = getenv("DORPATCH_FUSED_GEMM");
+    e->fused_gemm = e->bf16 && fg_env && atoi(fg_env) != 0;   // not validated on hardware yet: off unless asked for
     const char* pb_env = getenv("DORPATCH_POOL_BWD");
     // measured: rebuilding the d_stem patch in shared memory costs more than the saved HBM round trip
     // (2.25 ms vs 1.33 + 0.71 ms per 512-sample step) -> off unless DORPATCH_POOL_BWD=fused

@@ -55,6 +55,13 @@ void launch_stem_bwd_reduce(const void* dY, const void* w_krsc, int cin_pad, con
 void launch_stem_bwd_pool_reduce(const void* dpool, const int8_t* amax, const void* w_krsc, int cin_pad, const int16_t* rects,
                                  float* G, int B, int S, int n0, int n, int H, int W, cudaStream_t st);
 
+// ---- opt-in: GroupNorm+ReLU applied in the prologue of a tcgen05 1x1-convolution GEMM (kernels_gemm.cu, bf16)
+// out[m,n] = sum_k relu(gn(x))[m,k] * W[n,k] (+ shortcut[m,n]); `stats` from launch_gn_stats on x.
+bool gn_gemm_supported(int P, int K, int Nout);
+void launch_gn_gemm_pack(const void* w_nk, void* w_packed, int Nout, int K, cudaStream_t st);
+bool launch_gn_gemm_forward(const void* x, const void* w_packed, const float* stats, const float* gamma, const float* beta,
+                            const void* shortcut, void* out, int N, int P, int K, int Nout, cudaStream_t st);
+
 // ---- patch-side kernels (kernels_patch.cu) -------------------------------------------
 // utils.clip + add: adv_x = x + min(eps/||m(p-x)||,1) * m(p-x); l2[b], scale[b] dev outputs.
 void launch_paste(const float* x, const float* mask, const float* pattern, float* adv_x, float* l2, float* scale,
