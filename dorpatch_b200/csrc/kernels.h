@@ -32,12 +32,9 @@ void launch_maxpool_forward(const void* x, void* y, int8_t* amax, int N, int Hs,
                             cudaStream_t st);
 void launch_maxpool_backward(const void* dy, const int8_t* amax, void* dx, int N, int Hs, int Ws, int C, bool bf16,
                              cudaStream_t st);
-// head: pooled[n][c] = mean_p relu(gn(x)); logits = pooled @ Wfc^T + b
+// head: pooled[n][c] = mean_p relu(gn(x))  (the fc layer itself runs through cublasLt in the engine)
 void launch_head_pool(const void* x, const float* gamma, const float* beta, const float* stats, float* pooled,
                       int N, int P, int C, bool bf16, cudaStream_t st);
-void launch_fc_forward(const float* pooled, const float* w, const float* b, float* logits, int N, int C, int K,
-                       cudaStream_t st);
-void launch_fc_backward(const float* dlogits, const float* w, float* dpooled, int N, int C, int K, cudaStream_t st);
 // dy[n,p,c] = dpooled[n][c] / P
 void launch_pool_grad_bcast(const float* dpooled, void* dy, int N, int P, int C, bool bf16, cudaStream_t st);
 // strided spatial subsample [N,H,W,C] -> [N,H/2,W/2,C] (rows/cols 0,2,4,..) and its scatter-add adjoint

@@ -1087,39 +1087,6 @@ void launch_head_pool(const void* x, const float* gamma, const float* beta, cons
                        (const T*)x, gamma, beta, stats, pooled, P, C)));
 }
 
-// logits[n][k] = b[k] + sum_c pooled[n][c] * w[k][c]; one warp per (n,k)
-__global__ void fc_fwd_kernel(const float* __restrict__ pooled, const float* __restrict__ w,
-                              const float* __restrict__ b, float* __restrict__ logits, int N, int C, int K) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= N * K) return;
-  const int n = warp / K, k = warp % K;
-  const float* pn = pooled + (size_t)n * C;
-  const float* wk = w + (size_t)k * C;
-  float s = 0.f;
-  for (int c = lane; c < C; c += 32) s = fmaf(pn[c], wk[c], s);
-  s = warp_sum(s);
-  if (lane == 0) logits[(size_t)n * K + k] = s + b[k];
-}
-void launch_fc_forward(const float* pooled, const float* w, const float* b, float* logits, int N, int C, int K,
-                       cudaStream_t st) {
-  const size_t threads = (size_t)N * K * 32;
-  fc_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(pooled, w, b, logits, N, C, K);
-}
-// dpooled[n][c] = sum_k dlogits[n][k] * w[k][c]   (dlogits is almost all zeros: skip them)
-__global__ void fc_bwd_kernel(const float* __restrict__ dl, const float* __restrict__ w, float* __restrict__ dp,
-                              int N, int C, int K) {
-  const int n = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s = 0.f;
-  for (int k = 0; k < K; ++k) {
-    const float d = dl[(size_t)n * K + k];   // uniform across the CTA
-    if (d != 0.f) s = fmaf(d, w[(size_t)k * C + c], s);
-  }
-  dp[(size_t)n * C + c] = s;
-}
-void launch_fc_backward(const float* dlogits, const float* w, float* dpooled, int N, int C, int K, cudaStream_t st) {
-  fc_bwd_kernel<<<dim3((C + 255) / 256, N), 256, 0, st>>>(dlogits, w, dpooled, N, C, K);
-}
 template <typename T>
 __global__ void pool_grad_bcast_kernel(const float* __restrict__ dp, T* __restrict__ dy, int P, int C, size_t total_vec) {
   constexpr int V = Vec<T>::N;
