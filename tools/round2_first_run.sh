@@ -6,6 +6,11 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 O=gpurun_out
 
+# 0. access-pattern micro-benchmarks: where does the ~3.1 TB/s ceiling of the GroupNorm kernels come from?
+timeout 60 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o $O/membench tools/membench.cu > $O/r2_membench.log 2>&1 \
+  && timeout 120 $O/membench >> $O/r2_membench.log 2>&1
+cat $O/r2_membench.log; rm -f $O/membench
+
 # 1. first hardware run of the tcgen05 GroupNorm-prologue GEMM (kernels_gemm.cu); a hang must not take the box down
 DORPATCH_TEST_FUSED_GEMM=1 timeout 180 python -m pytest tests/test_gpu_fused_gemm.py -m gpu -x -q > $O/r2_fused_gemm_test.log 2>&1
 tail -5 $O/r2_fused_gemm_test.log
