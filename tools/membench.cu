@@ -2,6 +2,8 @@
 // at ~3.1 TB/s whatever the CTA shape while the driver's copy peak is 6.5 TB/s and K1's bulk stores reach 5.2.
 // Each pattern moves the same buffers; prints GB/s (bytes read + written).  Standalone:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o gpurun_out/membench tools/membench.cu && gpurun_out/membench
+#include <cooperative_groups.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -139,6 +141,113 @@ static float time_ms(F&& launch, int reps = 5) {
   return ms / reps;
 }
 
+// ---- E: gn_fwd_cluster_kernel rebuilt step by step on the slab pattern (bf16, [N][P][C], one cluster of CL CTAs
+//         per sample, CTA slab = P/CL rows).  STEP 0: cluster launch, slab copy only.  1: + the apply math
+//         (unpack, fma, relu, pack).  2: + the statistics pass over the slab in shared memory and a CTA reduction.
+//         3: + cluster.sync, DSMEM reduce of the partials, split cluster barrier at the end (= the product kernel).
+namespace cg = cooperative_groups;
+__device__ __forceinline__ void unpack8(uint4 v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+template <int STEP>
+__global__ void __launch_bounds__(512) slab_gn(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int P, int C) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank(), n = blockIdx.x / CL;
+  const uint32_t bar = smem_u32(sm);
+  float* part = reinterpret_cast<float*>(sm + 64);            // [32][2]
+  float* s_stat = reinterpret_cast<float*>(sm + 64 + 256);    // [32][2]
+  float* tp = reinterpret_cast<float*>(sm + 1024);            // [threads][2]
+  unsigned char* slab = sm + 1024 + 512 * 8;
+  const int p0 = (int)(((long long)P * rank) / CL), p1 = (int)(((long long)P * (rank + 1)) / CL), rows = p1 - p0;
+  const uint32_t bytes = (uint32_t)rows * C * 2;
+  const size_t base = ((size_t)n * P + p0) * C;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async();
+    mbar_expect(bar, bytes);
+    for (uint32_t o = 0; o < bytes; o += 32768) bulk_g2s(smem_u32(slab) + o, (const unsigned char*)(x + base) + o, bytes - o < 32768 ? bytes - o : 32768, bar);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+  const int cols = C / 8, rpi = (int)blockDim.x / cols, tcol = threadIdx.x % cols, trow = threadIdx.x / cols;
+  const uint4* srow = reinterpret_cast<const uint4*>(slab);
+  float sa[8], sb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sa[i] = 1.0f + 0.001f * i; sb[i] = 0.01f * i; }
+  if (STEP >= 2) {
+    float a[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = 0.f; q[i] = 0.f; }
+    for (int r = trow; r < rows; r += rpi) {
+      float f[8]; unpack8(srow[(size_t)r * cols + tcol], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+    }
+    float ta = 0.f, tq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ta += a[i]; tq += q[i]; }
+    tp[threadIdx.x * 2] = ta; tp[threadIdx.x * 2 + 1] = tq;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float s = 0.f, t = 0.f;
+      for (int j = threadIdx.x; j < (int)blockDim.x; j += 32) { s += tp[j * 2]; t += tp[j * 2 + 1]; }
+      part[threadIdx.x * 2] = s; part[threadIdx.x * 2 + 1] = t;
+    }
+    if (STEP >= 3) {
+      cluster.sync();
+      if (threadIdx.x < 32) {
+        float s = 0.f, t = 0.f;
+        for (int r = 0; r < CL; ++r) { const float* rp = cluster.map_shared_rank(part, r); s += rp[threadIdx.x * 2]; t += rp[threadIdx.x * 2 + 1]; }
+        s_stat[threadIdx.x * 2] = s; s_stat[threadIdx.x * 2 + 1] = t;
+      }
+      __syncthreads();
+      cluster.barrier_arrive();
+    } else {
+      __syncthreads();
+      if (threadIdx.x < 32) { s_stat[threadIdx.x * 2] = part[threadIdx.x * 2]; s_stat[threadIdx.x * 2 + 1] = part[threadIdx.x * 2 + 1]; }
+      __syncthreads();
+    }
+    const float m = s_stat[(tcol & 31) * 2] * 1e-30f, v = s_stat[(tcol & 31) * 2 + 1] * 1e-30f;   // keep the result live, ~0
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sa[i] += v; sb[i] -= m; }
+  }
+  uint4* drow = reinterpret_cast<uint4*>(y + base);
+  for (int r = trow; r < rows; r += rpi) {
+    uint4 v = srow[(size_t)r * cols + tcol];
+    if (STEP >= 1) {
+      float f[8]; unpack8(v, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaxf(fmaf(sa[i], f[i], sb[i]), 0.f);
+      v = pack8(f);
+    }
+    drow[(size_t)r * cols + tcol] = v;
+  }
+  if (STEP >= 3) { __syncthreads(); cluster.barrier_wait(); }
+}
+template <int STEP>
+static float run_slab_gn(const void* src, void* dst, int N, int P, int C, int CL, int threads, size_t* moved) {
+  const size_t slab = (((size_t)((P + CL - 1) / CL)) * C * 2 + 127) / 128 * 128, smem = 1024 + 512 * 8 + slab;
+  CK(cudaFuncSetAttribute(slab_gn<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(N * CL); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  *moved = (size_t)2 * N * P * C * 2;
+  return time_ms([&] { CK(cudaLaunchKernelEx(&cfg, slab_gn<STEP>, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, P, C)); });
+}
+
 int main() {
   const size_t bytes = (size_t)1 << 30;                 // 1 GiB in, 1 GiB out (>> L2)
   unsigned char *src, *dst; uint4* sink;
@@ -174,5 +283,15 @@ int main() {
         printf("ring4 %6u B  %d CTA/SM  %s        %8.0f GB/s\n", chunk, ctas, nm, gbs((mode == 2 ? 1.0 : 2.0) * bytes, ms));
       }
     }
+  // gn_fwd_cluster_kernel step by step: the two dominant shapes of the bench (chunk of 256 samples)
+  struct Shape { int P, C, CL, threads; } shapes[] = {{3136, 256, 8, 512}, {3136, 256, 8, 256}, {3136, 64, 4, 256}, {784, 512, 8, 256}};
+  for (auto& sh : shapes) {
+    const int N = (int)(bytes / ((size_t)sh.P * sh.C * 2));
+    size_t moved = 0; float ms;
+    ms = run_slab_gn<0>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%d x%3d  0 copy            %8.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
+    ms = run_slab_gn<1>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%d x%3d  1 + apply math    %8.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
+    ms = run_slab_gn<2>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%d x%3d  2 + statistics    %8.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
+    ms = run_slab_gn<3>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%d x%3d  3 + cluster reduce %7.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
+  }
   return 0;
 }
