@@ -238,6 +238,7 @@ template <int STEP>
 static float run_slab_gn(const void* src, void* dst, int N, int P, int C, int CL, int threads, size_t* moved) {
   const size_t slab = (((size_t)((P + CL - 1) / CL)) * C * 2 + 127) / 128 * 128, smem = 1024 + 512 * 8 + slab;
   CK(cudaFuncSetAttribute(slab_gn<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (CL > 8) CK(cudaFuncSetAttribute(slab_gn<STEP>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(N * CL); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
   cudaLaunchAttribute attr[1];
@@ -284,14 +285,14 @@ int main() {
       }
     }
   // gn_fwd_cluster_kernel step by step: the two dominant shapes of the bench (chunk of 256 samples)
-  struct Shape { int P, C, CL, threads; } shapes[] = {{3136, 256, 8, 512}, {3136, 256, 8, 256}, {3136, 64, 4, 256}, {784, 512, 8, 256}};
+  struct Shape { int P, C, CL, threads; } shapes[] = {{3136, 256, 8, 512}, {3136, 256, 8, 256}, {3136, 256, 16, 256}, {3136, 64, 4, 256}, {784, 512, 8, 256}};
   for (auto& sh : shapes) {
     const int N = (int)(bytes / ((size_t)sh.P * sh.C * 2));
     size_t moved = 0; float ms;
-    ms = run_slab_gn<0>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%d x%3d  0 copy            %8.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
-    ms = run_slab_gn<1>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%d x%3d  1 + apply math    %8.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
-    ms = run_slab_gn<2>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%d x%3d  2 + statistics    %8.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
-    ms = run_slab_gn<3>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%d x%3d  3 + cluster reduce %7.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
+    ms = run_slab_gn<0>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  0 copy            %8.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
+    ms = run_slab_gn<1>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  1 + apply math    %8.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
+    ms = run_slab_gn<2>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  2 + statistics    %8.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
+    ms = run_slab_gn<3>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  3 + cluster reduce %7.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
   }
   return 0;
 }
