@@ -157,7 +157,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return v;
 }
-template <int STEP>
+template <int STEP, int VAR>   // VAR 0: as the product; 1: 4 independent rows per loop trip (ILP); 2: 1 + packed fma.rn.relu.bf16x2 apply
 __global__ void __launch_bounds__(512) slab_gn(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int P, int C) {
   extern __shared__ __align__(128) unsigned char sm[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -188,10 +188,24 @@ __global__ void __launch_bounds__(512) slab_gn(const __nv_bfloat16* __restrict__
     float a[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a[i] = 0.f; q[i] = 0.f; }
-    for (int r = trow; r < rows; r += rpi) {
-      float f[8]; unpack8(srow[(size_t)r * cols + tcol], f);
+    if (VAR == 0) {
+      for (int r = trow; r < rows; r += rpi) {
+        float f[8]; unpack8(srow[(size_t)r * cols + tcol], f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { a[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+        for (int i = 0; i < 8; ++i) { a[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+      }
+    } else {
+      for (int r0 = trow; r0 < rows; r0 += 4 * rpi) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = r0 + u * rpi < rows ? srow[(size_t)(r0 + u * rpi) * cols + tcol] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float f[8]; unpack8(v[u], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { a[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+        }
+      }
     }
     float ta = 0.f, tq = 0.f;
 #pragma unroll
@@ -222,23 +236,53 @@ __global__ void __launch_bounds__(512) slab_gn(const __nv_bfloat16* __restrict__
     for (int i = 0; i < 8; ++i) { sa[i] += v; sb[i] -= m; }
   }
   uint4* drow = reinterpret_cast<uint4*>(y + base);
-  for (int r = trow; r < rows; r += rpi) {
-    uint4 v = srow[(size_t)r * cols + tcol];
-    if (STEP >= 1) {
-      float f[8]; unpack8(v, f);
+  if (VAR == 0) {
+    for (int r = trow; r < rows; r += rpi) {
+      uint4 v = srow[(size_t)r * cols + tcol];
+      if (STEP >= 1) {
+        float f[8]; unpack8(v, f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaxf(fmaf(sa[i], f[i], sb[i]), 0.f);
-      v = pack8(f);
+        for (int i = 0; i < 8; ++i) f[i] = fmaxf(fmaf(sa[i], f[i], sb[i]), 0.f);
+        v = pack8(f);
+      }
+      drow[(size_t)r * cols + tcol] = v;
     }
-    drow[(size_t)r * cols + tcol] = v;
+  } else {
+    uint32_t pa[4], pb[4];                                   // scale / shift as bf16x2 (VAR 2)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 ha = __floats2bfloat162_rn(sa[2 * i], sa[2 * i + 1]), hb = __floats2bfloat162_rn(sb[2 * i], sb[2 * i + 1]);
+      pa[i] = *reinterpret_cast<uint32_t*>(&ha); pb[i] = *reinterpret_cast<uint32_t*>(&hb);
+    }
+    for (int r0 = trow; r0 < rows; r0 += 4 * rpi) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = r0 + u * rpi < rows ? srow[(size_t)(r0 + u * rpi) * cols + tcol] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (STEP >= 1) {
+          if (VAR == 2) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(&v[u]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(w[i]) : "r"(pa[i]), "r"(w[i]), "r"(pb[i]));
+          } else {
+            float f[8]; unpack8(v[u], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaxf(fmaf(sa[i], f[i], sb[i]), 0.f);
+            v[u] = pack8(f);
+          }
+        }
+        if (r0 + u * rpi < rows) drow[(size_t)(r0 + u * rpi) * cols + tcol] = v[u];
+      }
+    }
   }
   if (STEP >= 3) { __syncthreads(); cluster.barrier_wait(); }
 }
-template <int STEP>
+template <int STEP, int VAR>
 static float run_slab_gn(const void* src, void* dst, int N, int P, int C, int CL, int threads, size_t* moved) {
   const size_t slab = (((size_t)((P + CL - 1) / CL)) * C * 2 + 127) / 128 * 128, smem = 1024 + 512 * 8 + slab;
-  CK(cudaFuncSetAttribute(slab_gn<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (CL > 8) CK(cudaFuncSetAttribute(slab_gn<STEP>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  CK(cudaFuncSetAttribute(slab_gn<STEP, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (CL > 8) CK(cudaFuncSetAttribute(slab_gn<STEP, VAR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(N * CL); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
   cudaLaunchAttribute attr[1];
@@ -246,7 +290,7 @@ static float run_slab_gn(const void* src, void* dst, int N, int P, int C, int CL
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   *moved = (size_t)2 * N * P * C * 2;
-  return time_ms([&] { CK(cudaLaunchKernelEx(&cfg, slab_gn<STEP>, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, P, C)); });
+  return time_ms([&] { CK(cudaLaunchKernelEx(&cfg, slab_gn<STEP, VAR>, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, P, C)); });
 }
 
 int main() {
@@ -289,10 +333,12 @@ int main() {
   for (auto& sh : shapes) {
     const int N = (int)(bytes / ((size_t)sh.P * sh.C * 2));
     size_t moved = 0; float ms;
-    ms = run_slab_gn<0>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  0 copy            %8.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
-    ms = run_slab_gn<1>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  1 + apply math    %8.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
-    ms = run_slab_gn<2>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  2 + statistics    %8.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
-    ms = run_slab_gn<3>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  3 + cluster reduce %7.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
+    ms = run_slab_gn<0, 0>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  0 copy            %8.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
+    ms = run_slab_gn<1, 0>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  1 + apply math    %8.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
+    ms = run_slab_gn<2, 0>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  2 + statistics    %8.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
+    ms = run_slab_gn<3, 0>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  3 + cluster reduce %7.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
+    ms = run_slab_gn<3, 1>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  3, 4 rows per trip  %7.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
+    ms = run_slab_gn<3, 2>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  3, + bf16x2 apply   %7.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
   }
   return 0;
 }
