@@ -293,6 +293,131 @@ static float run_slab_gn(const void* src, void* dst, int N, int P, int C, int CL
   return time_ms([&] { CK(cudaLaunchKernelEx(&cfg, slab_gn<STEP, VAR>, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, P, C)); });
 }
 
+// ---- F: gn_bwd_cluster_kernel step by step (x slab by TMA into shared memory, dy streamed from global twice with 4
+//         loads in flight, dx written).  STEP 0: dx = dy copy with the x slab loaded.  1: + the dx math of pass 2.
+//         2: + pass 1 (sum dg, sum dg*xhat) and the CTA reduction.  3: + cluster.sync / DSMEM reduce (= the product).
+//         VAR 1: algebraically leaner passes (sum dg*x instead of dg*xhat; dx = fma(dg, rs, fma(x, c1, c0))).
+template <int STEP, int VAR>
+__global__ void __launch_bounds__(512, 1) slab_gn_bwd(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                       __nv_bfloat16* __restrict__ dx, int P, int C) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank(), n = blockIdx.x / CL;
+  const uint32_t bar = smem_u32(sm);
+  float* part = reinterpret_cast<float*>(sm + 64);
+  float* s_stat = reinterpret_cast<float*>(sm + 64 + 256);
+  float* tp = reinterpret_cast<float*>(sm + 1024);
+  unsigned char* slab = sm + 1024 + 512 * 8;
+  const int p0 = (int)(((long long)P * rank) / CL), p1 = (int)(((long long)P * (rank + 1)) / CL), rows = p1 - p0;
+  const uint32_t bytes = (uint32_t)rows * C * 2;
+  const size_t base = ((size_t)n * P + p0) * C;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async();
+    mbar_expect(bar, bytes);
+    for (uint32_t o = 0; o < bytes; o += 32768) bulk_g2s(smem_u32(slab) + o, (const unsigned char*)(x + base) + o, bytes - o < 32768 ? bytes - o : 32768, bar);
+  }
+  __syncthreads();
+  const int cols = C / 8, rpi = (int)blockDim.x / cols, tcol = threadIdx.x % cols, trow = threadIdx.x / cols;
+  const uint4* srow = reinterpret_cast<const uint4*>(slab);
+  const uint4* gdy = reinterpret_cast<const uint4*>(dy + base);
+  uint4* gdx = reinterpret_cast<uint4*>(dx + base);
+  float ga[8], sa[8], sb[8];
+  const float mu = 0.01f, rs = 1.3f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { ga[i] = 1.0f + 0.01f * i; sa[i] = rs * ga[i]; sb[i] = 0.02f * i - mu * sa[i]; }
+  mbar_wait(bar, 0);
+  float m1 = 0.001f, m2 = 0.002f;
+  if (STEP >= 2) {
+    float a[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = 0.f; q[i] = 0.f; }
+    for (int r0 = trow; r0 < rows; r0 += 4 * rpi) {
+      uint4 vd[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) vd[u] = r0 + u * rpi < rows ? __ldg(gdy + (size_t)(r0 + u * rpi) * cols + tcol) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r0 + u * rpi < rows) {
+          float fx[8], fd[8]; unpack8(srow[(size_t)(r0 + u * rpi) * cols + tcol], fx); unpack8(vd[u], fd);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float pre = fmaf(sa[i], fx[i], sb[i]);
+            const float dg = pre > 0.f ? fd[i] * ga[i] : 0.f;
+            if (VAR == 0) { const float xh = (fx[i] - mu) * rs; a[i] += dg; q[i] = fmaf(dg, xh, q[i]); }
+            else { a[i] += dg; q[i] = fmaf(dg, fx[i], q[i]); }
+          }
+        }
+      }
+    }
+    float ta = 0.f, tq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ta += a[i]; tq += q[i]; }
+    tp[threadIdx.x * 2] = ta; tp[threadIdx.x * 2 + 1] = tq;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float s = 0.f, t = 0.f;
+      for (int j = threadIdx.x; j < (int)blockDim.x; j += 32) { s += tp[j * 2]; t += tp[j * 2 + 1]; }
+      part[threadIdx.x * 2] = s; part[threadIdx.x * 2 + 1] = t;
+    }
+    if (STEP >= 3) {
+      cluster.sync();
+      if (threadIdx.x < 32) {
+        float s = 0.f, t = 0.f;
+        for (int r = 0; r < CL; ++r) { const float* rp = cluster.map_shared_rank(part, r); s += rp[threadIdx.x * 2]; t += rp[threadIdx.x * 2 + 1]; }
+        s_stat[threadIdx.x * 2] = s; s_stat[threadIdx.x * 2 + 1] = t;
+      }
+      __syncthreads();
+      cluster.barrier_arrive();
+    } else {
+      __syncthreads();
+      if (threadIdx.x < 32) { s_stat[threadIdx.x * 2] = part[threadIdx.x * 2]; s_stat[threadIdx.x * 2 + 1] = part[threadIdx.x * 2 + 1]; }
+      __syncthreads();
+    }
+    m1 += s_stat[(tcol & 31) * 2] * 1e-30f; m2 += s_stat[(tcol & 31) * 2 + 1] * 1e-30f;
+  }
+  const float c1 = -rs * rs * m2, c0 = -rs * m1 - c1 * mu;      // VAR 1: dx = rs*dg + c1*x + c0
+  for (int r0 = trow; r0 < rows; r0 += 4 * rpi) {
+    uint4 vd[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) vd[u] = r0 + u * rpi < rows ? __ldg(gdy + (size_t)(r0 + u * rpi) * cols + tcol) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r0 + u * rpi < rows) {
+        uint4 out = vd[u];
+        if (STEP >= 1) {
+          float fx[8], fd[8], fo[8]; unpack8(srow[(size_t)(r0 + u * rpi) * cols + tcol], fx); unpack8(vd[u], fd);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float pre = fmaf(sa[i], fx[i], sb[i]);
+            const float dg = pre > 0.f ? fd[i] * ga[i] : 0.f;
+            if (VAR == 0) { const float xh = (fx[i] - mu) * rs; fo[i] = rs * (dg - m1 - xh * m2); }
+            else fo[i] = fmaf(dg, rs, fmaf(fx[i], c1, c0));
+          }
+          out = pack8(fo);
+        }
+        gdx[(size_t)(r0 + u * rpi) * cols + tcol] = out;
+      }
+    }
+  }
+  if (STEP >= 3) { __syncthreads(); cluster.barrier_wait(); }
+}
+template <int STEP, int VAR>
+static float run_slab_gn_bwd(const void* x, const void* dy, void* dx, int N, int P, int C, int CL, int threads, size_t* moved) {
+  const size_t slab = (((size_t)((P + CL - 1) / CL)) * C * 2 + 127) / 128 * 128, smem = 1024 + 512 * 8 + slab;
+  CK(cudaFuncSetAttribute(slab_gn_bwd<STEP, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (CL > 8) CK(cudaFuncSetAttribute(slab_gn_bwd<STEP, VAR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(N * CL); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  *moved = (size_t)3 * N * P * C * 2;                            // x + dy + dx (the second dy read is expected from L2)
+  return time_ms([&] { CK(cudaLaunchKernelEx(&cfg, slab_gn_bwd<STEP, VAR>, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, P, C)); });
+}
+
 int main() {
   const size_t bytes = (size_t)1 << 30;                 // 1 GiB in, 1 GiB out (>> L2)
   unsigned char *src, *dst; uint4* sink;
@@ -339,6 +464,16 @@ int main() {
     ms = run_slab_gn<3, 0>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  3 + cluster reduce %7.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
     ms = run_slab_gn<3, 1>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  3, 4 rows per trip  %7.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
     ms = run_slab_gn<3, 2>(src, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); printf("gn P=%4d C=%4d cl%-2d x%3d  3, + bf16x2 apply   %7.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, gbs((double)moved, ms));
+  }
+  // gn_bwd_cluster_kernel step by step (third buffer = dy)
+  unsigned char* src2; CK(cudaMalloc(&src2, bytes)); CK(cudaMemset(src2, 2, bytes));
+  Shape bshapes[] = {{3136, 256, 8, 512}, {3136, 256, 16, 256}, {784, 512, 8, 256}};
+  for (auto& sh : bshapes) {
+    const int N = (int)(bytes / ((size_t)sh.P * sh.C * 2));
+    size_t moved = 0; float ms;
+#define BW(STEP, VAR, NAME) ms = run_slab_gn_bwd<STEP, VAR>(src, src2, dst, N, sh.P, sh.C, sh.CL, sh.threads, &moved); \
+    printf("gn bwd P=%4d C=%4d cl%-2d x%3d  %-28s %7.0f GB/s\n", sh.P, sh.C, sh.CL, sh.threads, NAME, gbs((double)moved, ms));
+    BW(0, 0, "0 copy (x slab, dy -> dx)") BW(1, 0, "1 + dx math") BW(2, 0, "2 + pass 1 sums") BW(3, 0, "3 + cluster reduce") BW(3, 1, "3, leaner algebra")
   }
   return 0;
 }
