@@ -12,6 +12,8 @@
 // STATUS: opt-in (DORPATCH_FUSED_GEMM=1).  Written at the end of round 1 after the GPU budget was spent: it
 // compiles for sm_100a (UTCHMMA / UTCBAR / LDTM in the SASS) but has NOT run on hardware yet, so the engine
 // keeps the cublasLt + cluster-GroupNorm path by default.  First item of the round-2 list in DESIGN.md.
+// The two descriptor encodings below were compared bit for bit with cute::UMMA::SmemDescriptor / InstrDescriptor
+// filled field by field (host program against the vendored CUTLASS headers).
 //
 // Structure (one 128 x BN output tile per CTA, 192 threads):
 //   warps 0-3  A producers: 16-byte global loads of the raw x tile (8 in flight per thread), scale / shift /
