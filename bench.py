@@ -1,21 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- EOT-samples/sec of the DorPatch hot loop (BASELINE.json metric).
 
-    python bench.py [--gpus N --steps K --warmup W] [--impl native|reference]
+    python bench.py [--gpus N --steps K --warmup W] [--impl native|reference] [--precision tf32|bf16|fp32]
 
-A "step" is one iteration of attack.py:184-342 of the reference over one batch: sample occlusion
-masks on the host, paste + expand (K1), ResNetV2-50x1-BiT forward + backward-to-input (K2),
-CW loss (K4), masked EOT gradient reduce (K1^T), [all-reduce across ranks], host bookkeeping,
-sign step (K3).  Workload = BASELINE.json configs[1]: 32 synthetic 224x224 images x 16 EOT
-occlusion samples per GPU and step, 5 % patch budget (stage-1 step on a selected binary mask),
-untargeted, double-mask universe (2520).  Weak scaling: every GPU always processes 32 x 16
-samples, so the per-image EOT count is 16 x N.
+A "step" is one iteration of attack.py:184-342 of the reference over one batch: sample occlusion masks on the host,
+paste + expand (K1), ResNetV2-50x1-BiT forward + backward-to-input (K2), CW loss (K4), masked EOT gradient reduce
+(K1^T), [all-reduce across ranks], host bookkeeping, sign step (K3).
 
-Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = the same step
-through host buffers (H2D of x/mask/pattern + D2H of mask/pattern/losses every step),
-`roofline` = the hand-written K1 expand kernel against measured HBM copy bandwidth,
-`kernels` = per-category device time / achieved rate of one profiled step,
-`cpu_baseline` = the oracle port of the reference's step timed on this box's host cores.
+HEADLINE workload = BASELINE.json configs[2] ("c3", the largest single-GPU configuration): 64 synthetic 224x224 images
+x 32 EOT double-mask occlusion samples (dropout=2, the 2520-mask universe), stage-1 step, at the REFERENCE'S OWN GPU
+ARITHMETIC: fp32 storage, TF32 tensor-core convolutions (`--precision tf32`; PyTorch's cudnn.allow_tf32 default that
+the reference runs with).  Weak scaling keeps 2048 EOT samples per GPU and step: N=1 64x32, N=2 64x64, N=4 128x64,
+N=8 256x64 = configs[3] ("c4"); every rank holds all images and evaluates its slice of the EOT samples (one
+all-reduce of the patch gradient per step).
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = the same step through host buffers
+(H2D of x/mask/pattern + D2H of mask/pattern/losses every step, dp_attack_step_host), `roofline` = the hand-written K1
+kernel, timed on the variant and launch shape the step itself uses, against the measured HBM copy bandwidth,
+`kernels` = per-category device time / achieved rate of one profiled step, `cpu_baseline` = the oracle port of the
+reference's step on this box's host cores.  Extra legs (N=1 only; `legs`): the same step at bf16, configs[1] ("c2",
+32 x 16) at both precisions, the reference's default shape (1 image x 128 EOT), the stage-0 step of configs[4]
+("c5": targeted, 10 % budget, density + group-lasso regularisers live), PatchCleanser evaluation throughput, and the
+scan-amortised throughput (the reference re-scans the whole mask universe every 100 steps, attack.py:187-190).
 """
 import argparse
 import json
@@ -30,9 +36,26 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-IMG, B_PER_GPU, S_PER_GPU = 224, 32, 16
-GFLOP_PER_SAMPLE = 16.36        # 8.18 fwd + 8.18 dgrad
+IMG = 224
+SAMPLES_PER_GPU = 2048           # c3: 64 x 32
+GFLOP_PER_SAMPLE = 16.36         # 8.18 fwd + 8.18 dgrad
 METRIC, UNIT = "EOT-samples/sec", "samples/s"
+CONFIGS = {   # name -> (images, EOT per image [total], stage, targeted, budget)
+    "c3": dict(B=64, S=32, stage=1, targeted=False, budget=0.12),
+    "c2": dict(B=32, S=16, stage=1, targeted=False, budget=0.05),
+    "b1": dict(B=1, S=128, stage=1, targeted=False, budget=0.12),      # the reference's defaults (main.py:27, attack.py:52-53)
+    "c5s0": dict(B=32, S=16, stage=0, targeted=True, budget=0.10),     # configs[4] per-GPU share, stage-0 step
+}
+
+
+def shape_for(config, world):
+    c = dict(CONFIGS[config])
+    if config == "c3" and world > 1:              # weak scaling towards c4 (256 x 64 on 8 GPUs)
+        c["S"] = 64
+        c["B"] = SAMPLES_PER_GPU * world // 64
+    elif world > 1:
+        c["S"] = c["S"] * world
+    return c
 
 
 def peaks():
@@ -80,8 +103,8 @@ def cpu_step_factory(S):
     import torch
     from oracle import attack as OA, masks as OM, resnetv2 as OR
     params = OR.random_init(seed=0)
-    # "all the host threads it can use": torch-CPU convolutions on a 16-sample batch get SLOWER when
-    # oversubscribed (128 threads: 0.14 samples/s on the GPU box), so pick the fastest thread count.
+    # "all the host threads it can use": torch-CPU convolutions on a small batch get SLOWER when oversubscribed
+    # (128 threads: 0.14 samples/s on the GPU box), so pick the fastest thread count.
     cores = os.cpu_count() or 1
     cand = sorted({c for c in (8, 16, 32, 64, cores) if c <= min(cores, 64)})
     zt = torch.rand(4, 3, IMG, IMG).requires_grad_(True)
@@ -102,7 +125,7 @@ def cpu_step_factory(S):
     x = torch.rand(1, 3, IMG, IMG, generator=g)
     pattern = torch.rand(1, 3, IMG, IMG, generator=g)
     imp = torch.rand(1, 1, IMG, IMG, generator=g)
-    mask = OA.patch_selection(imp, 0.05)
+    mask = OA.patch_selection(imp, CONFIGS["c3"]["budget"])
     uni = torch.from_numpy(OM.rects_to_bool(OM.universe_rects(IMG, 2), IMG))
     lvx = OA.local_variance(x)[0].mean(1)
     with torch.no_grad():
@@ -119,11 +142,24 @@ def cpu_step_factory(S):
     return step, torch.get_num_threads()
 
 
+def workload_config(config, world, precision=None):
+    c = shape_for(config, world)
+    name = {"c3": "configs[2] (c3)" if world == 1 else "c3 weak-scaled towards configs[3] (c4 = 256 x 64 on 8 GPUs)",
+            "c2": "configs[1] (c2)", "b1": "reference default shape", "c5s0": "configs[4] (c5) per-GPU share, stage-0 step"}[config]
+    return {"workload": "%s: batch %d x %d EOT (%d samples per GPU and step), 224x224, ResNetV2-50x1-BiT random-init, %d%% patch budget, "
+                        "%s, stage-%d step, double-mask universe (2520)" % (name, c["B"], c["S"], c["B"] * c["S"] // world, round(c["budget"] * 100),
+                                                                             "targeted" if c["targeted"] else "untargeted", c["stage"]),
+            "images": c["B"], "eot_per_image_total": c["S"], "eot_per_image_per_gpu": c["S"] // world, "img": IMG,
+            "parallelism": "eot-shard x%d + 1 allreduce(patch grad)/step" % world,
+            "l2_policy": "inputs larger than L2 (>= 0.6 GB network input + tens of GB of activations per step)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    step, threads = cpu_step_factory(S_PER_GPU)
+    S = CONFIGS[args.config]["S"]
+    step, threads = cpu_step_factory(S)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -132,31 +168,108 @@ def run_reference(args):
         n += step()
     dt = time.perf_counter() - t0
     v = n / dt
-    sample = "1 image x %d EOT occlusion samples per step (same per-image work; B scaled 32->1), stage-1 step, fp32, weights requires_grad as the reference" % S_PER_GPU
+    sample = ("1 image x %d EOT occlusion samples per step (same per-image work as the native arm; B scaled to 1 -- the reference is "
+              "batch-size-1 only), stage-1 step, fp32, weights requires_grad as the reference" % S)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": workload_config(args.config, args.gpus),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def workload_config(n_gpus):
-    return {"workload": "configs[1]: batch 32 x 16 EOT per GPU, 224x224, ResNetV2-50x1-BiT random-init, 5% patch budget, "
-                        "untargeted, stage-1 step, double-mask universe (2520)",
-            "images_per_gpu": B_PER_GPU, "eot_per_image_per_gpu": S_PER_GPU, "eot_per_image_total": S_PER_GPU * n_gpus,
-            "img": IMG, "parallelism": "eot-shard x%d + 1 allreduce(patch grad)/step" % n_gpus,
-            "l2_policy": "inputs larger than L2 (>= 150 MB network input + ~15 GB activations per step)"}
-
-
 # ----------------------------------------------------------------------------------------------
+class Workload:
+    """One bench configuration on one engine: device-resident state, the host state machine, step / step_e2e."""
+
+    def __init__(self, eng, config, world, rank, dev, dist):
+        import torch
+        from dorpatch_b200 import masks as PM
+        from dorpatch_b200.attack import DorPatch, _ImageState
+        c = shape_for(config, world)
+        self.eng, self.world, self.rank, self.dev, self.dist = eng, world, rank, dev, dist
+        self.B, self.S, self.S_loc, self.stage = c["B"], c["S"], c["S"] // world, c["stage"]
+        B = self.B
+        g = torch.Generator().manual_seed(1234)
+        self.x = torch.rand(B, 3, IMG, IMG, generator=g).to(dev)
+        self.pattern = torch.rand(B, 3, IMG, IMG, generator=g).to(dev)
+        importance = torch.rand(B, 1, IMG, IMG, generator=g).to(dev)
+        # stage 1: budget-sized binary mask from patch_selection; stage 0: the soft importance map itself is learnable
+        self.mask = DorPatch().patch_selection(importance, c["budget"]) if self.stage == 1 else importance
+        self.G = torch.zeros_like(self.x)
+        self.table = PM.universe(IMG, 2)
+        self.n_mask = self.table.shape[0]
+        y = eng.predict(self.x).astype(np.int64)
+        if c["targeted"]:
+            y = (y + 1 + np.random.RandomState(5).randint(0, 998, B)) % 1000        # a target != the clean label
+        self.y, self.crit = y, [bool(c["targeted"])] * B
+        self.states = [_ImageState(0.01, 1e-3, y[b], c["targeted"], np.random.RandomState(1234 + b)) for b in range(B)]
+        self.PM = PM
+        self.hx = torch.empty(self.x.shape, pin_memory=True).copy_(self.x)
+        self.hm = torch.empty(self.mask.shape, pin_memory=True).copy_(self.mask)
+        self.hp = torch.empty(self.pattern.shape, pin_memory=True).copy_(self.pattern)
+        if world > 1:
+            self.dx, self.dm, self.dp_ = torch.empty_like(self.x), torch.empty_like(self.mask), torch.empty_like(self.pattern)
+
+    @property
+    def samples_per_step(self):
+        return self.B * self.S
+
+    def host_sample(self, i):
+        idx = np.stack([s.sample(i, self.n_mask, self.S)[0] for s in self.states])
+        return idx, self.PM.gather(self.table, idx[:, self.rank * self.S_loc:(self.rank + 1) * self.S_loc])
+
+    def finish(self, i, idx, r, G):
+        import torch
+        loss_adv = r["loss_adv"]
+        if self.world > 1:
+            from dorpatch_b200.attack import exchange_shards
+            loss_adv, _ = exchange_shards(self.dist, G, loss_adv, r["preds"])
+        target = r["group_lasso"] if self.stage == 0 else r["loss_struc"]
+        st_used = [s.structured for s in self.states]
+        cg_used = [s.coeff_group_lasso for s in self.states]
+        for b, s in enumerate(self.states):
+            s.bookkeeping(self.stage, i, loss_adv[b], idx[b], 0, target[b])
+        return np.full(self.B, 0.01, np.float32), st_used, cg_used
+
+    def step(self, i):
+        idx, rects = self.host_sample(i)
+        r = self.eng.attack_grad(self.x, self.mask, self.pattern, rects, self.y, self.crit, 0.1, 4.0, self.stage, self.G, S_total=self.S)
+        lr, st_used, cg_used = self.finish(i, idx, r, self.G)
+        self.eng.attack_update(self.x, self.mask, self.pattern, self.G, lr, st_used, cg_used, 1e-3, self.stage)
+
+    def step_e2e(self, i):
+        import torch
+        idx, rects = self.host_sample(i)
+        if self.world == 1:
+            lr = np.full(self.B, 0.01, np.float32)
+            st_used = [s.structured for s in self.states]
+            cg_used = [s.coeff_group_lasso for s in self.states]
+            r = self.eng.attack_step_host(self.hx.numpy(), self.hm.numpy(), self.hp.numpy(), rects, self.y, self.crit, 0.1, 4.0,
+                                          self.stage, lr, st_used, cg_used, 1e-3, S_total=self.S)
+            target = r["group_lasso"] if self.stage == 0 else r["loss_struc"]
+            for b, s in enumerate(self.states):
+                s.bookkeeping(self.stage, i, r["loss_adv"][b], idx[b], 0, target[b])
+        else:
+            self.dx.copy_(self.hx, non_blocking=True); self.dm.copy_(self.hm, non_blocking=True); self.dp_.copy_(self.hp, non_blocking=True)
+            r = self.eng.attack_grad(self.dx, self.dm, self.dp_, rects, self.y, self.crit, 0.1, 4.0, self.stage, self.G, S_total=self.S)
+            lr, st_used, cg_used = self.finish(i, idx, r, self.G)
+            self.eng.attack_update(self.dx, self.dm, self.dp_, self.G, lr, st_used, cg_used, 1e-3, self.stage)
+            self.hm.copy_(self.dm, non_blocking=True); self.hp.copy_(self.dp_, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def io_bytes(self):
+        B, S = self.B, self.S_loc
+        h2d = B * 7 * IMG * IMG * 4 + B * S * 32 + B * S * 5
+        d2h = B * 4 * IMG * IMG * 4 + B * S * 8 + B * 16
+        return int(h2d), int(d2h)
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
-    from dorpatch_b200 import masks as PM
-    from dorpatch_b200.attack import DorPatch, _ImageState
     from dorpatch_b200.engine import Engine
     from dorpatch_b200.resnetv2 import ResNetV2
 
@@ -172,74 +285,21 @@ def run_native(args):
             os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, (world, args.gpus)
-
-    B, S_loc = args.batch, args.eot
-    S = S_loc * world
     pk = peaks()
-    eng = Engine(img=IMG, precision=args.precision, chunk=args.chunk, max_images=B, device=local, autotune=True)
     net = ResNetV2(seed=0)
-    eng.load_state_dict(net.state_dict())
+    sd = net.state_dict()
+    engines = {}
 
-    g = torch.Generator().manual_seed(1234)
-    x = torch.rand(B, 3, IMG, IMG, generator=g).to(dev)
-    pattern = torch.rand(B, 3, IMG, IMG, generator=g).to(dev)
-    importance = torch.rand(B, 1, IMG, IMG, generator=g).to(dev)
-    mask = DorPatch().patch_selection(importance, 0.05)                 # 5 % budget binary mask (stage 1)
-    G = torch.zeros_like(x)
-    table = PM.universe(IMG, 2)
-    n_mask = table.shape[0]
-    y = eng.predict(x).astype(np.int64)
-    np.random.seed(1234)
-    states = [_ImageState(0.01, 1e-3, y[b], False, np.random.RandomState(1234 + b)) for b in range(B)]
-    stage = 1
-
-    def host_sample(i):
-        idx = np.stack([s.sample(i, n_mask, S)[0] for s in states])
-        return idx, PM.gather(table, idx[:, rank * S_loc:(rank + 1) * S_loc])
-
-    def finish(i, idx, r):
-        loss_adv = r["loss_adv"]
-        if world > 1:
-            dist.all_reduce(G)
-            pack = torch.from_numpy(loss_adv).to(dev)
-            outs = [torch.empty_like(pack) for _ in range(world)]
-            dist.all_gather(outs, pack)
-            loss_adv = np.concatenate([o.cpu().numpy() for o in outs], 1)
-        lr = np.zeros(B, np.float32)
-        st_used = [s.structured for s in states]
-        for b, s in enumerate(states):
-            s.bookkeeping(stage, i, loss_adv[b], idx[b], 0, r["loss_struc"][b])
-            lr[b] = 0.01
-        return lr, st_used
-
-    def step(i):
-        idx, rects = host_sample(i)
-        r = eng.attack_grad(x, mask, pattern, rects, y, [False] * B, 0.1, 4.0, stage, G, S_total=S)
-        lr, st_used = finish(i, idx, r)
-        eng.attack_update(x, mask, pattern, G, lr, st_used, None, 1e-3, stage)
-
-    # pinned host mirrors for the end-to-end leg
-    hx = torch.empty(x.shape, pin_memory=True).copy_(x)
-    hm = torch.empty(mask.shape, pin_memory=True).copy_(mask)
-    hp = torch.empty(pattern.shape, pin_memory=True).copy_(pattern)
-    dx, dm, dp_ = torch.empty_like(x), torch.empty_like(mask), torch.empty_like(pattern)
-
-    def step_e2e(i):
-        idx, rects = host_sample(i)
-        if world == 1:
-            lr = np.full(B, 0.01, np.float32)
-            st_used = [s.structured for s in states]
-            r = eng.attack_step_host(hx.numpy(), hm.numpy(), hp.numpy(), rects, y, [False] * B, 0.1, 4.0, stage, lr,
-                                     st_used, None, 1e-3, S_total=S)
-            for b, s in enumerate(states):
-                s.bookkeeping(stage, i, r["loss_adv"][b], idx[b], 0, r["loss_struc"][b])
-        else:
-            dx.copy_(hx, non_blocking=True); dm.copy_(hm, non_blocking=True); dp_.copy_(hp, non_blocking=True)
-            r = eng.attack_grad(dx, dm, dp_, rects, y, [False] * B, 0.1, 4.0, stage, G, S_total=S)
-            lr, st_used = finish(i, idx, r)
-            eng.attack_update(dx, dm, dp_, G, lr, st_used, None, 1e-3, stage)
-            hm.copy_(dm, non_blocking=True); hp.copy_(dp_, non_blocking=True)
-            torch.cuda.synchronize()
+    def engine(precision):
+        if precision not in engines:
+            for e in engines.values():                  # one engine's workspace at a time
+                e.close()
+            engines.clear()
+            e = Engine(img=IMG, precision=precision, chunk=args.chunk, max_images=max(shape_for(args.config, world)["B"], 64),
+                       device=local, autotune=True)
+            e.load_state_dict(sd)
+            engines[precision] = e
+        return engines[precision]
 
     def barrier():
         torch.cuda.synchronize()
@@ -247,7 +307,7 @@ def run_native(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, K, i0):
+    def timed(eng, fn, K, i0):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = eng.launch_count
@@ -262,67 +322,100 @@ def run_native(args):
         return float(ms.item()), eng.launch_count - l0
 
     W, K = max(args.warmup, 3), args.steps
-    for i in range(W):
-        step(i)
-    if args.ncu:       # one step between cudaProfilerStart/Stop for `ncu --profile-from-start off`
-        rects_all = PM.gather(table, np.stack([np.random.RandomState(b).choice(n_mask, S_loc, replace=False) for b in range(B)]))
-        eng.expand(x, S_loc, rects_all)                       # warm-up of the standalone K1 launch (whole step batch)
+
+    def measure(precision, config, K, e2e=True, sampler=None):
+        eng = engine(precision)
+        wl = Workload(eng, config, world, rank, dev, dist if world > 1 else None)
+        for i in range(W):
+            wl.step(i)
+        if sampler is not None:
+            sampler.start()
+            time.sleep(0.3)
+        ms, launches = timed(eng, wl.step, K, W)
+        clocks = sampler.stop() if sampler is not None else None
+        res = dict(value=wl.samples_per_step * K / (ms / 1e3), ms_per_step=ms / K, launches=int(launches), clocks=clocks, wl=wl, eng=eng)
+        if e2e:
+            for i in range(2):
+                wl.step_e2e(W + K + i)
+            ms_e2e, _ = timed(eng, wl.step_e2e, K, W + K + 2)
+            res["e2e_value"] = wl.samples_per_step * K / (ms_e2e / 1e3)
+            res["e2e_ms"] = ms_e2e / K
+        return res
+
+    if args.ncu:       # W warm-up steps, then ONE step inside cudaProfilerStart/Stop (for `ncu --profile-from-start off`)
+        eng = engine(args.precision)
+        wl = Workload(eng, args.config, world, rank, dev, None)
+        for i in range(W):
+            wl.step(i)
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        step(W)
-        eng.expand(x, S_loc, rects_all)                       # the launch bench.py's `roofline` times
+        wl.step(W)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
-    ms, launches = timed(step, K, W)
-    clocks = sampler.stop()
-    for i in range(2):
-        step_e2e(W + K + i)
-    ms_e2e, _ = timed(step_e2e, K, W + K + 2)
-    N_step = B * S_loc * world
-    value = N_step * K / (ms / 1e3)
-    e2e_value = N_step * K / (ms_e2e / 1e3)
-    es = eng.elem_bytes
-    h2d = B * 7 * IMG * IMG * 4 + B * S_loc * 32 + B * S_loc * 5
-    d2h = B * 4 * IMG * IMG * 4 + B * S_loc * 8 + B * 16
 
+    head = measure(args.precision, args.config, K, e2e=True, sampler=ClockSampler(local))
+    wl, eng = head["wl"], head["eng"]
+    h2d, d2h = wl.io_bytes()
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.precision, "data": "synthetic", "config": workload_config(world),
-        "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h),
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic", "config": workload_config(args.config, world),
+        "clocks": head["clocks"], "gpu_launches": head["launches"],
+        "e2e": {"value": head["e2e_value"], "unit": UNIT, "ms_per_step": head["e2e_ms"], "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h,
                 "path": "dp_attack_step_host (C ABI, host buffers)" if world == 1 else "pinned host -> H2D -> grad/allreduce/update -> D2H"},
-        "engine": {"chunk": args.chunk, "c_pad": eng.c_pad, "device_bytes": eng.device_bytes},
+        "engine": {"chunk": args.chunk, "c_pad": eng.c_pad, "device_bytes": eng.device_bytes,
+                   "gn": os.environ.get("DORPATCH_GN", "v2"), "fused_gemm": os.environ.get("DORPATCH_FUSED_GEMM", "0")},
+        "precision_note": "tf32 = fp32 storage + TF32 tensor-core convolutions, the reference's own GPU arithmetic (torch cudnn.allow_tf32 "
+                          "default); bf16 legs are reported under `legs` and are backed by tests/test_gpu_attack_success.py",
     }
 
-    if rank == 0:
-        # ---- K1 roofline: the hand-written expand kernel alone on the whole step batch -------------
-        Nk = B * S_loc
-        rects_all = PM.gather(table, np.stack([np.random.RandomState(b).choice(n_mask, S_loc, replace=False) for b in range(B)]))
-        eng.expand(x, S_loc, rects_all)                                       # warm-up + allocation
+    def kernel_table(eng, wl, i):
+        eng.profile(True, reset=True)
+        wl.step(i)
         torch.cuda.synchronize()
-        buf = torch.empty((Nk, IMG, IMG, eng.c_pad), dtype=torch.bfloat16 if es == 2 else torch.float32, device=dev)
+        prof = eng.profile_read()
+        eng.profile(False)
+        tot = sum(v["ms"] for v in prof.values()) or 1.0
+        kern = {}
+        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+            d = {"ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 4), "launch_groups": v["count"]}
+            if v["flops"] > 0 and ("conv" in k or "gemm" in k):
+                d["tflops"] = round(v["flops"] / v["ms"] / 1e9, 1)
+                d["frac_of_bf16_peak"] = round(v["flops"] / v["ms"] / 1e9 / pk["tf_burst"], 3)
+            else:
+                d["gbs_algorithmic"] = round(v["bytes"] / v["ms"] / 1e6, 1)
+                d["frac_of_hbm_peak"] = round(v["bytes"] / v["ms"] / 1e6 / pk["hbm"], 3)
+            kern[k] = d
+        return kern, round(tot, 3)
+
+    # profiled step (all ranks execute it to keep collectives matched)
+    kern, ktot = kernel_table(eng, wl, W + 2 * K + 10)
+
+    if rank == 0:
+        es = eng.elem_bytes
+        # ---- K1 roofline: the variant the step launches (paste fused in, 7 input planes, one launch per classifier chunk)
+        #      on exactly that launch shape; CUDA events around back-to-back launches over rotating outputs > L2 --------
         import ctypes as C
         from dorpatch_b200 import _lib
-        ra = np.ascontiguousarray(rects_all.reshape(Nk, 4, 4), np.int16)
-        ra_dev = torch.from_numpy(ra).to(dev)
+        B, S_loc = wl.B, wl.S_loc
+        n_chunk = min(args.chunk, B * S_loc)
+        rects_all = wl.PM.gather(wl.table, np.stack([np.random.RandomState(b).choice(wl.n_mask, S_loc, replace=False) for b in range(B)]))
+        ra_dev = torch.from_numpy(np.ascontiguousarray(rects_all.reshape(B * S_loc, 4, 4), np.int16)).to(dev)
+        dt_t = torch.bfloat16 if es == 2 else torch.float32
+        n_rot = max(2, int(400e6 // (n_chunk * IMG * IMG * eng.c_pad * es)) + 1)      # rotate over > 400 MB of outputs
+        bufs = [torch.empty((n_chunk, IMG, IMG, eng.c_pad), dtype=dt_t, device=dev) for _ in range(n_rot)]
+        eng.paste(wl.x, wl.mask, wl.pattern, 4.0)                                 # the clip scale the fused variant reads
+        n_starts = list(range(0, B * S_loc - n_chunk + 1, n_chunk)) or [0]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        buf2 = torch.empty_like(buf)
-        bufs = (buf, buf2)
 
         def k1_launch(i, rp):
-            _lib.check(eng.lib.dp_expand_dev(eng.handle, C.c_void_p(x.data_ptr()), B, S_loc, rp, C.c_void_p(bufs[i & 1].data_ptr()), eng._stream()))
+            _lib.check(eng.lib.dp_expand_step_dev(eng.handle, C.c_void_p(wl.x.data_ptr()), C.c_void_p(wl.mask.data_ptr()),
+                                                  C.c_void_p(wl.pattern.data_ptr()), B, S_loc, rp, n_starts[i % len(n_starts)], n_chunk,
+                                                  C.c_void_p(bufs[i % n_rot].data_ptr()), eng._stream()))
 
         def k1_time(rp, pairs, per_pair=10):
-            # dp_expand_dev = exactly one kernel launch (rectangles already on the device).  Average launch duration
-            # over `per_pair` back-to-back launches per CUDA-event pair (a single 40 us launch between two events also
-            # measures ~5 us of event / launch latency); the launches alternate between two 154 MB outputs (each > L2),
-            # so no launch finds its lines in cache.  Median over the pairs.
             for i in range(4):
                 k1_launch(i, rp)
             torch.cuda.synchronize()
@@ -336,91 +429,110 @@ def run_native(args):
                 ts.append(e0.elapsed_time(e1) / per_pair)
             return float(np.median(ts))
 
-        k1_ms = k1_time(C.c_void_p(ra_dev.data_ptr()), 7)
+        rp_dev = C.c_void_p(ra_dev.data_ptr())
+        k1_ms = k1_time(rp_dev, 7)
         k1_ms_clean = k1_time(None, 3)                         # diagnostic: same launch without occluders (pure bulk-store path)
-        e0.record()                                            # single launch per event pair, for comparison with earlier rounds
-        k1_launch(0, C.c_void_p(ra_dev.data_ptr()))
-        e1.record()
-        torch.cuda.synchronize()
+        e0.record(); k1_launch(0, rp_dev); e1.record(); torch.cuda.synchronize()
         k1_ms_single = e0.elapsed_time(e1)
-        tw = []                                                # context: write-only ceiling (cudaMemset of the same buffer)
-        for _ in range(8):
-            e0.record()
-            buf.zero_()
-            e1.record()
-            torch.cuda.synchronize()
-            tw.append(e0.elapsed_time(e1))
-        write_only_gbs = buf.numel() * buf.element_size() / float(np.median(tw)) / 1e6
-        alg_bytes = Nk * IMG * IMG * 3 * es + B * 3 * IMG * IMG * 4
-        act_bytes = Nk * IMG * IMG * eng.c_pad * es + B * 3 * IMG * IMG * 4
-        traffic = None
+        img_in_launch = max(1, n_chunk // S_loc)
+        alg_bytes = n_chunk * IMG * IMG * 3 * es + img_in_launch * 7 * IMG * IMG * 4
+        traffic, tnote = None, None
         tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")     # dram bytes of this launch from the last ncu --set full capture
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if tj.get("samples") == Nk and tj.get("dtype") == args.precision:
-                traffic = tj.get("dram_bytes")
-        out["roofline"] = {"kernel": "expand_kernel (K1: paste/normalise/occlude, TMA bulk tiles)", "bound": "hbm",
-                           "achieved": alg_bytes / k1_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
-                           "frac": alg_bytes / k1_ms / 1e6 / pk["hbm"], "traffic": traffic,
-                           "achieved_incl_channel_pad": act_bytes / k1_ms / 1e6, "ms": k1_ms, "ms_single_launch_event_pair": k1_ms_single,
-                           "timing": "CUDA events around 10 back-to-back launches, alternating two outputs, median of 7",
-                           "unoccluded_gbs": alg_bytes / k1_ms_clean / 1e6, "write_only_memset_gbs": write_only_gbs,
-                           "algorithmic_bytes_per_launch": alg_bytes, "peak_source": pk["src"]}
-        # ---- forward-only universe scan (collect_failure, attack.py:384-406): every mask of the universe for a
-        #      few images through dp_predict; the reference runs it once per image every 100 steps ---------------
+            if tj.get("samples") == n_chunk and tj.get("dtype") == args.precision:
+                traffic, tnote = tj.get("dram_bytes"), tj.get("note")
+        out["roofline"] = {"kernel": "expand_kernel<FUSED=1> (K1: paste + L2-scale + normalise + occlude, TMA bulk tiles), the in-step variant",
+                           "bound": "hbm", "achieved": alg_bytes / k1_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
+                           "frac": alg_bytes / k1_ms / 1e6 / pk["hbm"], "traffic": traffic, "traffic_note": tnote,
+                           "ms": k1_ms, "ms_single_launch_event_pair": k1_ms_single, "samples_per_launch": n_chunk,
+                           "timing": "CUDA events around 10 back-to-back launches rotating over %d output buffers (> L2 in total), median of 7" % n_rot,
+                           "unoccluded_gbs": alg_bytes / k1_ms_clean / 1e6,
+                           "algorithmic_bytes_per_launch": alg_bytes,
+                           "algorithmic_bytes_per_unit": "3*224*224*%d B written per EOT sample + 7*224*224*4 B read per image (SURVEY 8d)" % es,
+                           "peak_source": pk["src"]}
+        del bufs
+        out["roofline_step"] = {"bound": "tensor", "achieved": GFLOP_PER_SAMPLE * head["value"] / world / 1e3, "peak": pk["tf_sus"],
+                                "unit": "TFLOP/s", "frac": GFLOP_PER_SAMPLE * head["value"] / world / 1e3 / pk["tf_sus"],
+                                "note": "16.36 GFLOP (fwd+dgrad) per EOT sample x per-GPU samples/s vs sustained bf16 cuBLAS peak (TF32 peak is half of it)"}
+        out["kernels"] = kern
+        out["kernels_total_ms"] = ktot
+        out["kernels_note"] = "one step profiled with CUDA events around every launch, chunks serialised on ONE lane; the timed steps overlap two lanes (two streams), so ms_per_step < kernels_total_ms"
+        # ---- forward-only universe scan (collect_failure, attack.py:384-406) + PatchCleanser evaluation (c3 names it) ----
         try:
-            Bs = min(B, 4)
-            rects_scan = PM.gather(table, np.tile(np.arange(n_mask), (Bs, 1)))
-            eng.predict(x[:Bs], n_mask, rects_scan)                               # warm-up (plans for the tail chunk)
+            Bs = 4
+            rects_scan = wl.PM.gather(wl.table, np.tile(np.arange(wl.n_mask), (Bs, 1)))
+            eng.predict(wl.x[:Bs], wl.n_mask, rects_scan)
             ts = []
             for _ in range(3):
-                e0.record()
-                eng.predict(x[:Bs], n_mask, rects_scan)
-                e1.record()
-                torch.cuda.synchronize()
+                e0.record(); eng.predict(wl.x[:Bs], wl.n_mask, rects_scan); e1.record(); torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
             scan_ms_img = float(np.median(ts)) / Bs
-            out["scan"] = {"fwd_samples_per_s": n_mask / (scan_ms_img / 1e3), "masks": int(n_mask), "ms_per_image": scan_ms_img,
-                           "amortised_eot_samples_per_s": N_step / ((ms / K + scan_ms_img * B / 100.0 / world) / 1e3),
-                           "note": "dp_predict over the whole mask universe; amortised = one scan per image every 100 steps, the universe split over the ranks (attack.scan_failures)"}
-        except Exception as ex:                                             # the scan is a side figure: never lose the bench line over it
-            out["scan"] = {"error": str(ex)[:200]}
-        # ---- whole-step tensor roofline + per-category breakdown of one profiled step -------------------
-        out["roofline_step"] = {"bound": "tensor", "achieved": GFLOP_PER_SAMPLE * value / world / 1e3, "peak": pk["tf_sus"],
-                                "unit": "TFLOP/s", "frac": GFLOP_PER_SAMPLE * value / world / 1e3 / pk["tf_sus"],
-                                "note": "16.36 GFLOP (fwd+dgrad) per EOT sample x per-GPU samples/s vs sustained bf16 cuBLAS peak"}
-    # profiled step (all ranks execute it to keep collectives matched)
-    eng.profile(True, reset=True)
-    step(W + 2 * K + 10)
-    torch.cuda.synchronize()
-    prof = eng.profile_read()
-    eng.profile(False)
+            amort = wl.samples_per_step / ((head["ms_per_step"] + scan_ms_img * wl.B / 100.0 / world) / 1e3)
+            out["scan"] = {"fwd_samples_per_s": wl.n_mask / (scan_ms_img / 1e3), "masks": int(wl.n_mask), "ms_per_image": scan_ms_img,
+                           "amortised_eot_samples_per_s": amort,
+                           "note": "dp_predict over the whole mask universe; amortised = `value` with one scan per image every 100 steps added (attack.py:187-190), the universe split over the ranks"}
+            out["value_scan_amortised"] = amort
+            from dorpatch_b200.defenses.PatchCleanser import MaskWindow, PatchCleanser
+            from dorpatch_b200.utils import NormModel, get_normalize
+            import contextlib, io
+            net_native = ResNetV2(seed=0)
+            net_native._engines = {}
+            model = torch.nn.DataParallel(NormModel(net_native, get_normalize("imagenet", "resnetv2")))
+            net_native.adopt_engine(eng)
+            with contextlib.redirect_stdout(io.StringIO()):
+                defs = [PatchCleanser(MaskWindow(IMG, r, 1), model) for r in (0.015, 0.03, 0.06, 0.12)]
+            l0 = eng.launch_count
+            t0 = time.perf_counter()
+            n_img = 2
+            for im in wl.x[:n_img]:
+                for d in defs:
+                    d.robust_predict(im, True)
+            torch.cuda.synchronize()
+            dtp = time.perf_counter() - t0
+            out["patchcleanser_eval"] = {"images_per_s": n_img / dtp, "ms_per_image_4_ratios": dtp / n_img * 1e3,
+                                         "note": "defenses/PatchCleanser.py:68-112 on dp_predict: 36 single + 630 double masks (+ second round) x 4 ratios per image (main.py:61,151)"}
+        except Exception as ex:                                             # side figures: never lose the bench line over them
+            out.setdefault("scan", {"error": str(ex)[:300]})
+            out["patchcleanser_eval"] = {"error": str(ex)[:300]}
+    del wl
+    # ---- extra legs (single GPU only; each is a full timed run of K2 steps) ----------------------------------------------
+    if world == 1 and not args.no_legs:
+        legs = {}
+        K2 = max(3, min(K, 10))
+        other = "bf16" if args.precision != "bf16" else "tf32"
+        plan = [(args.precision, "c2"), (args.precision, "b1"), (args.precision, "c5s0"), (other, "c3"), (other, "c2"), (other, "b1")]
+        for prec, cfg in plan:
+            if cfg == args.config and prec == args.precision:
+                continue
+            try:
+                r = measure(prec, cfg, K2 if cfg != "b1" else 20, e2e=(cfg in ("c2", "c3")))
+                leg = {"value": r["value"], "ms_per_step": r["ms_per_step"], "gpu_launches": r["launches"], "dtype": prec,
+                       "config": workload_config(cfg, 1)["workload"]}
+                if "e2e_value" in r:
+                    leg["e2e"] = r["e2e_value"]
+                if cfg == "c2" and prec == "bf16":
+                    leg["kernels"], leg["kernels_total_ms"] = kernel_table(r["eng"], r["wl"], 1000)
+                legs["%s_%s" % (prec, cfg)] = leg
+                del r
+            except Exception as ex:
+                legs["%s_%s" % (prec, cfg)] = {"error": str(ex)[:300]}
+        out["legs"] = legs
+    for e in engines.values():
+        e.close()
     if rank == 0:
-        tot = sum(v["ms"] for v in prof.values()) or 1.0
-        kern = {}
-        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
-            d = {"ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 4), "launch_groups": v["count"]}
-            if v["flops"] > 0 and ("conv" in k or "gemm" in k):
-                d["tflops"] = round(v["flops"] / v["ms"] / 1e9, 1)
-                d["frac_of_bf16_peak"] = round(v["flops"] / v["ms"] / 1e9 / pk["tf_burst"], 3)
-            else:
-                d["gbs_algorithmic"] = round(v["bytes"] / v["ms"] / 1e6, 1)
-                d["frac_of_hbm_peak"] = round(v["bytes"] / v["ms"] / 1e6 / pk["hbm"], 3)
-            kern[k] = d
-        out["kernels"] = kern
-        out["kernels_total_ms"] = round(tot, 3)
-        out["kernels_note"] = "one step profiled with CUDA events around every launch, chunks serialised on ONE lane; the timed steps overlap two lanes (two streams), so ms_per_step < kernels_total_ms"
         # ---- CPU baseline: oracle port on this box's host cores, bounded sample ----------------------------
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cstep, threads = cpu_step_factory(S_PER_GPU)
+                S = CONFIGS[args.config]["S"]
+                cstep, threads = cpu_step_factory(S)
                 cstep()
                 t0, n = time.perf_counter(), 0
                 while time.perf_counter() - t0 < args.cpu_seconds:
                     n += cstep()
-                dt = time.perf_counter() - t0
-                out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                                       "sample": "%d steps of 1 image x %d EOT samples (%.1f s), stage-1 step, fp32 torch-CPU oracle port, weight grads on as in the reference" % (n // S_PER_GPU, S_PER_GPU, dt)}
+                dtc = time.perf_counter() - t0
+                out["cpu_baseline"] = {"value": n / dtc, "unit": UNIT, "cores": threads, "kind": "port",
+                                       "sample": "%d steps of 1 image x %d EOT samples (%.1f s), stage-1 step, fp32 torch-CPU oracle port, weight grads on as in the reference" % (n // S, S, dtc)}
             except Exception as ex:   # the bench line must survive a CPU-side problem
                 out["cpu_baseline"] = {"error": repr(ex)}
         print(json.dumps(out))
@@ -435,12 +547,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DORPATCH_PRECISION", "bf16"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("DORPATCH_BENCH_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("DORPATCH_CHUNK", "256")))
-    ap.add_argument("--batch", type=int, default=B_PER_GPU)
-    ap.add_argument("--eot", type=int, default=S_PER_GPU)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the extra legs (bf16 / c2 / B=1 / stage 0)")
     ap.add_argument("--ncu", action="store_true", help="run W warm-up steps, then ONE step inside cudaProfilerStart/Stop, and exit")
     args = ap.parse_args()
     if args.impl == "reference":

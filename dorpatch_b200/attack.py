@@ -160,13 +160,24 @@ def exchange_shards(dist, G, loss_adv, preds):
     S) and an all-gather of the per-sample results [B,S/world] -> [B,S] in rank order, so every
     rank takes the identical bookkeeping decisions and the identical sign step."""
     world = dist.get_world_size()
-    dist.all_reduce(G)
-    pack = torch.from_numpy(np.concatenate([loss_adv, preds.astype(np.float32)], 1)).to(G.device)
-    outs = [torch.empty_like(pack) for _ in range(world)]
-    dist.all_gather(outs, pack)
+    # the all-reduce is enqueued first and asynchronously (NCCL's own stream); the small gather and its single
+    # device->host copy run while it is in flight, and the sign step (next on the compute stream) waits for it.
+    work = dist.all_reduce(G, async_op=True)
     s_loc = loss_adv.shape[1]
-    loss_all = np.concatenate([o[:, :s_loc].cpu().numpy() for o in outs], 1)
-    preds_all = np.concatenate([o[:, s_loc:].cpu().numpy() for o in outs], 1).astype(np.int32)
+    pack = torch.from_numpy(np.concatenate([loss_adv, preds.astype(np.float32)], 1))
+    if G.is_cuda:
+        pack = pack.pin_memory().to(G.device, non_blocking=True)
+        allp = torch.empty((world,) + tuple(pack.shape), dtype=pack.dtype, device=G.device)
+        dist.all_gather_into_tensor(allp, pack)
+        allp = allp.cpu()                                   # one D2H + one synchronisation for all ranks' results
+    else:                                                   # gloo (CPU tests)
+        outs = [torch.empty_like(pack) for _ in range(world)]
+        dist.all_gather(outs, pack)
+        allp = torch.stack(outs)
+    work.wait()
+    allp = allp.numpy()
+    loss_all = np.concatenate([allp[r][:, :s_loc] for r in range(world)], 1)
+    preds_all = np.concatenate([allp[r][:, s_loc:] for r in range(world)], 1).astype(np.int32)
     return loss_all, preds_all
 
 
@@ -205,7 +216,9 @@ class DorPatch(object):
                  selection='topk', dropout=2, sampling_size=128, density=1e-3, structured=1e-3, eps=4., dual=False,
                  eot_affine=0.0, eot_colour=0.0, eot_seed=0, **kwargs):
         """Reference signature (attack.py:51-53) plus three opt-in keywords for the affine / colour
-        EOT extension (default 0 = off = the reference's behaviour)."""
+        EOT extension (default 0 = off = the reference's behaviour).  `image_seeds=[s_0..s_{B-1}]` (keyword)
+        makes row b of a B > 1 call replay the B == 1 run seeded with s_b (parity of the
+        batched configs is defined per image against a B == 1 reference run)."""
         if basic_unit != 7:
             raise NotImplementedError("the native kernels are built for basic_unit=7")
         if selection != 'topk':
@@ -222,8 +235,19 @@ class DorPatch(object):
         dist = _dist()
         rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
 
-        adv_mask = torch.rand([B, 1, H, W]).to(dev)              # attack.py:59 (CPU generator)
-        adv_pattern = torch.rand(x.shape).to(dev)                # attack.py:60
+        image_seeds = kwargs.get("image_seeds")
+        if image_seeds is not None and len(image_seeds) != B:
+            raise ValueError("image_seeds needs one seed per image")
+        if image_seeds is None:
+            adv_mask = torch.rand([B, 1, H, W]).to(dev)          # attack.py:59 (CPU generator)
+            adv_pattern = torch.rand(x.shape).to(dev)            # attack.py:60
+        else:
+            # row b reproduces a B == 1 run preceded by utils.set_random_seed(image_seeds[b]): its own torch-CPU
+            # generator for the two initial draws and its own legacy numpy stream for the mask sampling
+            gens = [torch.Generator().manual_seed(int(s)) for s in image_seeds]
+            mp = [(torch.rand([1, 1, H, W], generator=g), torch.rand([1, 3, H, W], generator=g)) for g in gens]
+            adv_mask = torch.cat([m for m, _ in mp]).to(dev)
+            adv_pattern = torch.cat([q for _, q in mp]).to(dev)
         mask_best = torch.zeros_like(adv_mask)
         pattern_best = torch.zeros_like(adv_pattern)
         if y is None:                                            # attack.py:67-69
@@ -242,7 +266,9 @@ class DorPatch(object):
         S_loc = S // world
         all_rects = _masks.gather(table, np.arange(n_mask))      # [n_mask,4,4] for the scans
 
-        if B == 1:
+        if image_seeds is not None:
+            rngs = [np.random.RandomState(int(s)) for s in image_seeds]
+        elif B == 1:
             rngs = [np.random]                                   # the global legacy stream, as the reference
         else:
             rngs = [np.random.RandomState(int(np.random.randint(0, 2 ** 31 - 1))) for _ in range(B)]
@@ -436,19 +462,10 @@ class DorPatch(object):
                 f = ~f
             failed = np.nonzero(f.any(0))[0].tolist()
         else:
-            n = mask_set_universe.size(0)
-            failed = []
-            with torch.no_grad():
-                for j in range(int(np.ceil(n / batch_size))):
-                    ms = mask_set_universe[j * batch_size: min((j + 1) * batch_size, n)]
-                    xm = (adv_x[:, None] * ms + 0.5 * ~ms).view((-1,) + adv_x.shape[1:])
-                    if transforms is not None:
-                        xm = transforms(xm)
-                    preds = model(xm).argmax(-1)
-                    f = preds == y.view((adv_x.shape[0], batch_size))[:, :ms.size(0)].reshape(-1)
-                    if targeted:
-                        f = ~f
-                    failed.append((f.nonzero().view(-1) % ms.size(0) + j * batch_size).unique())
-                failed = torch.cat(failed, 0).cpu().numpy().tolist()
+            # the reference's bool universe [n,1,H,W] (True = keep): every mask is "all but <= 4 rectangles", which is
+            # what the native K1 kernel consumes -- recover the rectangles and take the same dp_predict path
+            if transforms is not None:
+                raise NotImplementedError("collect_failure(transforms=...) is an unused hook of the reference (attack.py:395-396)")
+            return self.collect_failure(adv_x, y, _masks.from_bool(mask_set_universe), targeted, model, batch_size)
         print(">> %d failures collected!" % len(failed))
         return failed

@@ -72,7 +72,7 @@ struct ConvW {            // one convolution's weights (device, KRSC, activation
   cudnnFilterDescriptor_t wdesc = nullptr;
   cudnnConvolutionDescriptor_t cdesc = nullptr;
 };
-struct GNW { int C = 0; float* gamma = nullptr; float* beta = nullptr; };
+struct GNW { int C = 0; float* gamma = nullptr; float* beta = nullptr; bool pos = false; };   // pos: every gamma > 0 (packed bf16 ReLU gate allowed)
 struct Block {
   int cin, mid, cout, stride, hin, hout;
   bool has_ds;
@@ -172,6 +172,7 @@ struct dp_engine {
   float* adv_x = nullptr; float* dLs = nullptr; float* scale = nullptr; float* l2 = nullptr;
   float* loss_struc = nullptr; float* loss_density = nullptr; float* group_lasso = nullptr;
   float* win_dev = nullptr; float* grp_ss = nullptr;
+  float* helper_scale = nullptr; float* helper_l2 = nullptr; float* helper_ws = nullptr;   // scratch of dp_paste(out) / dp_window_sum
   float* lr_d = nullptr; float* structured_d = nullptr; float* coeff_d = nullptr;
   float* host_x = nullptr; float* host_mask = nullptr; float* host_pattern = nullptr; float* host_G = nullptr;  // dp_attack_step_host
 
@@ -362,8 +363,9 @@ struct dp_engine {
     host_pattern = (float*)dmalloc(B * 3 * HW * 4);
     host_mask = (float*)dmalloc(B * HW * 4);
     host_G = (float*)dmalloc(B * 3 * HW * 4);
-    for (float** p : {&scale, &l2, &loss_struc, &loss_density, &group_lasso, &lr_d, &structured_d, &coeff_d})
+    for (float** p : {&scale, &l2, &loss_struc, &loss_density, &group_lasso, &lr_d, &structured_d, &coeff_d, &helper_scale, &helper_l2})
       *p = (float*)dmalloc(B * 4);
+    helper_ws = (float*)dmalloc(B * HW * 4);
     win_dev = (float*)dmalloc(B * 64 * 4);
     grp_ss = (float*)dmalloc(B * (H / UNIT) * (H / UNIT) * 4);
     ensure_samples(chunk);
@@ -382,6 +384,11 @@ struct dp_engine {
   void upload_vec(float* dst, const float* host, int64_t numel, int64_t want) {
     if (numel != want) fail("vector numel %lld != expected %lld", (long long)numel, (long long)want);
     CUDA_OK(cudaMemcpy(dst, host, (size_t)numel * 4, cudaMemcpyHostToDevice));
+  }
+  void upload_gamma(GNW& g_, const float* host, int64_t numel) {
+    upload_vec(g_.gamma, host, numel, g_.C);
+    g_.pos = true;
+    for (int64_t i = 0; i < numel; ++i) g_.pos = g_.pos && (host[i] > 0.f);
   }
   void load_weights(int n, const char* const* names, const float* const* ptrs, const int64_t* numels) {
     std::map<std::string, int> idx;
@@ -412,15 +419,15 @@ struct dp_engine {
           dp::launch_gn_gemm_pack(b.c3.w, b.c3p, b.cout, b.mid, st); KERNEL_OK();
           CUDA_OK(cudaStreamSynchronize(st));
         }
-        i = get(P("norm1.weight")); upload_vec(b.n1.gamma, ptrs[i], numels[i], b.cin);
+        i = get(P("norm1.weight")); upload_gamma(b.n1, ptrs[i], numels[i]);
         i = get(P("norm1.bias")); upload_vec(b.n1.beta, ptrs[i], numels[i], b.cin);
-        i = get(P("norm2.weight")); upload_vec(b.n2.gamma, ptrs[i], numels[i], b.mid);
+        i = get(P("norm2.weight")); upload_gamma(b.n2, ptrs[i], numels[i]);
         i = get(P("norm2.bias")); upload_vec(b.n2.beta, ptrs[i], numels[i], b.mid);
-        i = get(P("norm3.weight")); upload_vec(b.n3.gamma, ptrs[i], numels[i], b.mid);
+        i = get(P("norm3.weight")); upload_gamma(b.n3, ptrs[i], numels[i]);
         i = get(P("norm3.bias")); upload_vec(b.n3.beta, ptrs[i], numels[i], b.mid);
         if (++bi == DEPTHS[s]) { bi = 0; ++s; }
       }
-      i = get("norm.weight"); upload_vec(head_gn.gamma, ptrs[i], numels[i], WIDTHS[3]);
+      i = get("norm.weight"); upload_gamma(head_gn, ptrs[i], numels[i]);
       i = get("norm.bias"); upload_vec(head_gn.beta, ptrs[i], numels[i], WIDTHS[3]);
       i = get("head.fc.weight"); upload_vec(fc_w, ptrs[i], numels[i], (int64_t)K * WIDTHS[3]);
       i = get("head.fc.bias"); upload_vec(fc_b, ptrs[i], numels[i], K);
@@ -676,7 +683,7 @@ struct dp_engine {
     gemm(N, last.cout, K, 3, fc_w, dlog, nullptr, 0.f, dpooled, st);           // dpooled = dlogits * Wfc (fp32)
     PROF(this, "head_bwd", 2.0 * N * pl * last.cout * es, 0, st, {
       dp::launch_pool_grad_bcast(dpooled, GB, N, pl, last.cout, bf16, st);
-      dp::launch_gn_relu_backward(GB, last.out, nullptr, GA, head_gn.gamma, head_gn.beta, head_stats, gn_partial, N, pl, last.cout, bf16, st);
+      dp::launch_gn_relu_backward(GB, last.out, nullptr, GA, head_gn.gamma, head_gn.beta, head_stats, gn_partial, N, pl, last.cout, bf16, st, head_gn.pos);
     }); KERNEL_OK(); launches += 3;
     for (int bi = (int)blocks.size() - 1; bi >= 0; --bi) {
       Block& b = blocks[bi];
@@ -686,10 +693,10 @@ struct dp_engine {
       // d_a3 = d_out * W3
       gemm(N * pout, b.mid, b.cout, 1, b.c3.w, GA, nullptr, 0.f, GB, st);
       PROF(this, "gn_relu_bwd", 3.0 * N * pout * b.mid * es, 0, st,
-           dp::launch_gn_relu_backward(GB, b.h2, nullptr, GC, b.n3.gamma, b.n3.beta, b.st3, gn_partial, N, pout, b.mid, bf16, st)); KERNEL_OK(); launches += 2;
+           dp::launch_gn_relu_backward(GB, b.h2, nullptr, GC, b.n3.gamma, b.n3.beta, b.st3, gn_partial, N, pout, b.mid, bf16, st, b.n3.pos)); KERNEL_OK(); launches += 2;
       conv_bwd(lid, b.c2, N, b.hin, b.hout, GC, GB, st);
       PROF(this, "gn_relu_bwd", 3.0 * N * pin_ * b.mid * es, 0, st,
-           dp::launch_gn_relu_backward(GB, b.h1, nullptr, GC, b.n2.gamma, b.n2.beta, b.st2, gn_partial, N, pin_, b.mid, bf16, st)); KERNEL_OK(); launches += 2;
+           dp::launch_gn_relu_backward(GB, b.h1, nullptr, GC, b.n2.gamma, b.n2.beta, b.st2, gn_partial, N, pin_, b.mid, bf16, st, b.n2.pos)); KERNEL_OK(); launches += 2;
       gemm(N * pin_, b.cin, b.mid, 1, b.c1.w, GC, nullptr, 0.f, GB, st);          // d_xp (conv1 path)
       if (b.has_ds) {
         if (b.stride == 2) {
@@ -699,10 +706,10 @@ struct dp_engine {
           gemm(N * pout, b.cin, b.cout, 1, b.ds.w, GA, nullptr, 1.f, GB, st);    // accumulate
         }
         PROF(this, "gn_relu_bwd", 3.0 * N * pin_ * b.cin * es, 0, st,
-             dp::launch_gn_relu_backward(GB, xin, nullptr, GD, b.n1.gamma, b.n1.beta, b.st1, gn_partial, N, pin_, b.cin, bf16, st)); KERNEL_OK(); launches += 2;
+             dp::launch_gn_relu_backward(GB, xin, nullptr, GD, b.n1.gamma, b.n1.beta, b.st1, gn_partial, N, pin_, b.cin, bf16, st, b.n1.pos)); KERNEL_OK(); launches += 2;
       } else {
         PROF(this, "gn_relu_bwd", 4.0 * N * pin_ * b.cin * es, 0, st,
-             dp::launch_gn_relu_backward(GB, xin, GA, GD, b.n1.gamma, b.n1.beta, b.st1, gn_partial, N, pin_, b.cin, bf16, st)); KERNEL_OK(); launches += 2;
+             dp::launch_gn_relu_backward(GB, xin, GA, GD, b.n1.gamma, b.n1.beta, b.st1, gn_partial, N, pin_, b.cin, bf16, st, b.n1.pos)); KERNEL_OK(); launches += 2;
       }
       std::swap(GA, GD);
     }
@@ -910,9 +917,13 @@ int32_t dp_paste(dp_engine* e, const float* x, const float* mask, const float* p
   e->check_B(B);
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_OK(cudaSetDevice(e->cfg.device));
-  dp::launch_paste(x, mask, pattern, adv_x_out ? adv_x_out : e->adv_x, e->l2, e->scale, B, e->H, e->H, eps, st); KERNEL_OK(); ++e->launches;
-  if (l2_host) CUDA_OK(cudaMemcpyAsync(l2_host, e->l2, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  if (scale_host) CUDA_OK(cudaMemcpyAsync(scale_host, e->scale, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  // with an output buffer this is the stand-alone helper (utils.clip, main.py:140): it must not disturb the per-step
+  // state (adv_x, clip scale) a dp_attack_grad left behind for dp_attack_update; without one it IS the step's paste
+  float* l2d = adv_x_out ? e->helper_l2 : e->l2;
+  float* scd = adv_x_out ? e->helper_scale : e->scale;
+  dp::launch_paste(x, mask, pattern, adv_x_out ? adv_x_out : e->adv_x, l2d, scd, B, e->H, e->H, eps, st); KERNEL_OK(); ++e->launches;
+  if (l2_host) CUDA_OK(cudaMemcpyAsync(l2_host, l2d, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  if (scale_host) CUDA_OK(cudaMemcpyAsync(scale_host, scd, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   if (l2_host || scale_host) CUDA_OK(cudaStreamSynchronize(st));
   DP_CATCH
 }
@@ -925,7 +936,7 @@ int32_t dp_window_sum(dp_engine* e, const float* t, int32_t B, int32_t k, int32_
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_OK(cudaSetDevice(e->cfg.device));
   const size_t n = (size_t)B * (e->H / k) * (e->H / k);
-  float* tmp = e->dLs;   // scratch: at most B*H*W floats
+  float* tmp = e->helper_ws;   // own scratch (never the structural-loss gradient the sign step reads)
   dp::launch_window_sum(t, tmp, B, e->H, e->H, k, square != 0, st); KERNEL_OK(); ++e->launches;
   CUDA_OK(cudaMemcpyAsync(out_host, tmp, n * 4, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
@@ -956,6 +967,21 @@ int32_t dp_expand_dev(dp_engine* e, const float* img, int32_t B, int32_t S, cons
   const int N = B * S;
   PROF(e, "expand_k1", (double)N * e->H * e->H * 3 * e->es + 3.0 * e->H * e->H * 4 * (double)B, 0, st,
        dp::launch_expand(img, nullptr, nullptr, nullptr, nullptr, rects_dev, out, B, S, 0, N, e->H, e->H, e->Cp, e->bf16, false, e->num_sms, st));
+  KERNEL_OK(); ++e->launches;
+  DP_CATCH
+}
+
+int32_t dp_expand_step_dev(dp_engine* e, const float* x, const float* mask, const float* pattern, int32_t B, int32_t S,
+                           const int16_t* rects_dev, int32_t n0, int32_t n, void* out, void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  if (!out || !x || !mask || !pattern) fail("dp_expand_step_dev: null pointer");
+  if (n0 < 0 || n < 1 || n0 + n > B * S) fail("dp_expand_step_dev: samples [%d, %d) outside [0, %d)", n0, n0 + n, B * S);
+  e->check_B(B);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  PROF(e, "expand_k1", (double)n * e->H * e->H * 3 * e->es + 7.0 * e->H * e->H * 4 * (double)n / S, 0, st,
+       dp::launch_expand(nullptr, x, mask, pattern, e->scale, rects_dev, out, B, S, n0, n, e->H, e->H, e->Cp, e->bf16, true, e->num_sms, st));
   KERNEL_OK(); ++e->launches;
   DP_CATCH
 }
@@ -1180,6 +1206,54 @@ int32_t dp_net_forward_backward(dp_engine* e, const float* z, int32_t N, float* 
     e->backward(N, dlogits_dev, st);
     dp::launch_unpack_nhwc(e->d_input, dz_dev, N, e->H, e->H, e->Cpd, e->bf16, st); KERNEL_OK(); ++e->launches;
   }
+  DP_CATCH
+}
+
+/* ---- op-level test hooks (tests/test_gpu_ops.py) ------------------------------------------------------ */
+int32_t dp_debug_stem_bwd_reduce(dp_engine* e, const void* dY, const int16_t* rects_host, int32_t B, int32_t S, float* G,
+                                 void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  if (!e->own_stem) fail("dp_debug_stem_bwd_reduce: the fused stem backward exists for the bf16 engine only");
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = B * S;
+  e->h2d_samples(rects_host, N, st);
+  CUDA_OK(cudaMemsetAsync(G, 0, (size_t)B * 3 * e->H * e->H * 4, st));
+  dp::launch_stem_bwd_reduce(dY, e->stem.w, e->stem.cin_pad, rects_host ? e->rects_d : nullptr, G, B, S, 0, N, e->H, e->H, st);
+  KERNEL_OK(); ++e->launches;
+  DP_CATCH
+}
+
+int32_t dp_debug_gn_gemm(dp_engine* e, const void* x, const void* w_nk, const float* stats, const float* gamma, const float* beta,
+                         const void* shortcut, void* out, int32_t N, int32_t P, int32_t K, int32_t Nout, void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!dp::gn_gemm_supported(P, K, Nout)) fail("dp_debug_gn_gemm: shape P=%d K=%d Nout=%d not supported by the tcgen05 kernel", P, K, Nout);
+  void* packed = nullptr;
+  CUDA_OK(cudaMalloc(&packed, (size_t)Nout * K * 2));
+  dp::launch_gn_gemm_pack(w_nk, packed, Nout, K, st);
+  const bool ok = dp::launch_gn_gemm_forward(x, packed, stats, gamma, beta, shortcut, out, N, P, K, Nout, st);
+  cudaError_t err = cudaStreamSynchronize(st);
+  cudaFree(packed);
+  if (!ok) fail("dp_debug_gn_gemm: launch refused");
+  CUDA_OK(err);
+  KERNEL_OK(); e->launches += 2;
+  DP_CATCH
+}
+
+int32_t dp_debug_gn(dp_engine* e, const void* x, const void* dy, const void* addend, const float* gamma, const float* beta,
+                    int32_t gamma_positive, void* y, void* dx, float* stats, int32_t N, int32_t P, int32_t C, void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N > e->chunk) fail("dp_debug_gn: N=%d exceeds chunk=%d (statistics scratch)", N, e->chunk);
+  dp::launch_gn_relu_forward(x, y, gamma, beta, e->gn_partial, stats, N, P, C, e->bf16, st); KERNEL_OK();
+  if (dy != nullptr) { dp::launch_gn_relu_backward(dy, x, addend, dx, gamma, beta, stats, e->gn_partial, N, P, C, e->bf16, st, gamma_positive != 0); KERNEL_OK(); }
+  e->launches += 4;
   DP_CATCH
 }
 

@@ -10,6 +10,8 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -1152,10 +1154,524 @@ void launch_subsample2_adjoint_add(const void* dy, void* dx, int N, int H, int W
   });
 }
 
+
+// ====================================================================================
+// GroupNorm v2 (round 2): the same cluster-per-sample scheme, rebuilt for instruction count.
+// ncu of v1 (profiles/r02_gn_v1_ncu.txt): DRAM traffic = algorithmic, but 330 warp-instructions per
+// 16-byte (x, dy) vector pair at IPC 1.5 -- 64-bit address arithmetic, per-row bound / chunk checks and
+// per-element unpack + gate dominate; the kernels are issue-bound, not HBM-bound.  v2:
+//   * a CTA's slab is a LINEAR array of 16-byte vectors; thread t owns vectors t, t + T, t + 2T, ... (its channel
+//     column is fixed because T % (C/V) == 0), so the loops carry one 32-bit offset and no row / column arithmetic;
+//   * the TMA load completes on one mbarrier per 32 KB chunk and the loops walk whole chunks (IPC iterations,
+//     fully unrolled: IPC independent shared / global loads in flight per thread), tail handled once;
+//   * bf16: unpack = 1 shift / 1 mask per element, ReLU folded into cvt.rn.relu.bf16x2.f32, the backward ReLU gate
+//     is ONE packed compare (x > thr_c, thr_c = -sb/sa rounded DOWN to bf16 so that the test is exact on bf16
+//     inputs) + one AND per element PAIR; channels with sa <= 0 take the generic fp32 gate (whole-kernel variant);
+//   * backward statistics as sum(dy*gate) and sum(dy*gate*x) per channel (gamma, mean, rstd applied once per thread
+//     after the loop); backward apply as dx = k1_c*dym + k2_g*x + k3_g: 2 FMA per element.
+// Statistics and every sum stay fp32.
+// ====================================================================================
+namespace gn2 {
+constexpr uint32_t CHUNK = 32768;
+constexpr int MAX_CHUNKS = 7;                      // <= 224 KB per slab
+constexpr int OFF_BAR_X = 0, OFF_BAR_D = 64, OFF_PART = 128, OFF_SA = 384, OFF_SB = 512, OFF_FLAG = 640;
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint32_t bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar)); }
+__device__ __forceinline__ void bar_wait(uint32_t bar) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(0u)
+        : "memory");
+  }
+}
+// thread 0: one bulk copy + one mbarrier per 32 KB chunk of a contiguous slab
+__device__ __forceinline__ void load_slab(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar0) {
+  int k = 0;
+  for (uint32_t off = 0; off < bytes; off += CHUNK, ++k) {
+    const uint32_t nb = bytes - off < CHUNK ? bytes - off : CHUNK;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * k), "r"(nb) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+                 "l"((const char*)src + off), "r"(nb), "r"(bar0 + 8 * k)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ float blo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bhi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_relu(float lo, float hi) {   // {relu(hi), relu(lo)} -> bf16x2
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t gt2_mask(uint32_t a, uint32_t b) {   // 0xffff per half where a > b (bf16x2)
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+}
+// largest bf16 <= t (as the high half of a float): x > t  <=>  x > floor_bf16(t) for every bf16 x
+__device__ __forceinline__ uint32_t floor_bf16_bits(float t) {
+  uint32_t u = __float_as_uint(t);
+  if ((u & 0xffffu) != 0u && (u >> 31)) u += 0x10000u;   // negative: truncation rounds towards zero = up -> step one down
+  return u >> 16;
+}
+
+template <typename T> struct Acc;   // per-vector math on the raw 16 bytes
+template <> struct Acc<float> {
+  static constexpr int V = 4;
+  static __device__ __forceinline__ void unpack(const uint4& v, float* f) {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+  }
+  static __device__ __forceinline__ uint4 apply_relu(const uint4& v, const float* sa, const float* sb) {
+    float f[4]; unpack(v, f);
+    uint4 o;
+    o.x = __float_as_uint(fmaxf(fmaf(sa[0], f[0], sb[0]), 0.f)); o.y = __float_as_uint(fmaxf(fmaf(sa[1], f[1], sb[1]), 0.f));
+    o.z = __float_as_uint(fmaxf(fmaf(sa[2], f[2], sb[2]), 0.f)); o.w = __float_as_uint(fmaxf(fmaf(sa[3], f[3], sb[3]), 0.f));
+    return o;
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+  }
+};
+template <> struct Acc<__nv_bfloat16> {
+  static constexpr int V = 8;
+  static __device__ __forceinline__ void unpack(const uint4& v, float* f) {
+    f[0] = blo(v.x); f[1] = bhi(v.x); f[2] = blo(v.y); f[3] = bhi(v.y); f[4] = blo(v.z); f[5] = bhi(v.z); f[6] = blo(v.w); f[7] = bhi(v.w);
+  }
+  static __device__ __forceinline__ uint4 apply_relu(const uint4& v, const float* sa, const float* sb) {
+    float f[8]; unpack(v, f);
+    uint4 o;
+    o.x = pack_relu(fmaf(sa[0], f[0], sb[0]), fmaf(sa[1], f[1], sb[1]));
+    o.y = pack_relu(fmaf(sa[2], f[2], sb[2]), fmaf(sa[3], f[3], sb[3]));
+    o.z = pack_relu(fmaf(sa[4], f[4], sb[4]), fmaf(sa[5], f[5], sb[5]));
+    o.w = pack_relu(fmaf(sa[6], f[6], sb[6]), fmaf(sa[7], f[7], sb[7]));
+    return o;
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+  }
+};
+
+// Deterministic CTA reduction of per-thread per-channel accumulators to per-group sums (as gnc::cta_group_reduce,
+// for a linear thread -> column mapping: column = threadIdx.x % cols).
+template <int V>
+__device__ __forceinline__ void group_reduce(const float* a, const float* b, int C, float* tp, float* part) {
+  gnc::cta_group_reduce<V>(a, b, C, tp, part);   // identical indexing: thread t = row * cols + column
+}
+
+// ---- forward --------------------------------------------------------------------------------------
+template <typename T, int TH>
+__global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                                    const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta,
+                                                                    float* __restrict__ stats, int P, int C) {
+  using A = Acc<T>;
+  constexpr int V = A::V;
+  constexpr int IPC = (int)(CHUNK / (TH * 16));       // iterations per 32 KB chunk (8 / 4)
+  extern __shared__ __align__(128) unsigned char smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int n = blockIdx.x / CL;
+  const uint32_t sb0 = s32(smem);
+  float* part = reinterpret_cast<float*>(smem + OFF_PART);
+  float* s_mean = reinterpret_cast<float*>(smem + OFF_SA);
+  float* s_rstd = reinterpret_cast<float*>(smem + OFF_SB);
+  float* tp = reinterpret_cast<float*>(smem + gnc::HDR);
+  const uint32_t slab = sb0 + (uint32_t)(gnc::HDR + gnc::tp_bytes(TH));
+
+  const int p0 = (int)(((long long)P * rank) / CL), p1 = (int)(((long long)P * (rank + 1)) / CL);
+  const uint32_t slab_bytes = (uint32_t)((size_t)(p1 - p0) * C * sizeof(T));
+  const size_t gbase = ((size_t)n * P + p0) * C * sizeof(T);          // byte offset of the slab in x / y
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < MAX_CHUNKS; ++k) bar_init(sb0 + OFF_BAR_X + 8 * k);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    load_slab(slab, reinterpret_cast<const char*>(x) + gbase, slab_bytes, sb0 + OFF_BAR_X);
+  }
+  const int cols = C / V, cpg = C / GN_GROUPS;
+  const int tcol = threadIdx.x % cols;
+  const uint32_t nvec = slab_bytes >> 4;
+  const uint32_t iters = nvec / TH, rem = nvec % TH;                  // thread t: vectors t + j*TH, j < iters (+1 if t < rem)
+  const uint32_t full_chunks = iters / IPC;
+  const uint32_t n_chunks = (slab_bytes + CHUNK - 1) / CHUNK;
+  __syncthreads();                                                    // barrier inits visible before anyone polls
+
+  float a[V], bq[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { a[i] = 0.f; bq[i] = 0.f; }
+  uint32_t sp = slab + threadIdx.x * 16;
+  for (uint32_t k = 0; k < full_chunks; ++k) {
+    bar_wait(sb0 + OFF_BAR_X + 8 * k);
+    uint4 v[IPC];
+#pragma unroll
+    for (int j = 0; j < IPC; ++j) v[j] = lds128(sp + j * TH * 16);
+#pragma unroll
+    for (int j = 0; j < IPC; ++j) {
+      float f[V]; A::unpack(v[j], f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { a[i] += f[i]; bq[i] = fmaf(f[i], f[i], bq[i]); }
+    }
+    sp += IPC * TH * 16;
+  }
+  for (uint32_t k = full_chunks; k < n_chunks; ++k) bar_wait(sb0 + OFF_BAR_X + 8 * k);   // tail: everything has landed
+  for (uint32_t j = full_chunks * IPC; j < iters + (threadIdx.x < rem ? 1u : 0u); ++j) {
+    const uint4 v = lds128(slab + (j * TH + threadIdx.x) * 16);
+    float f[V]; A::unpack(v, f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { a[i] += f[i]; bq[i] = fmaf(f[i], f[i], bq[i]); }
+  }
+  group_reduce<V>(a, bq, C, tp, part);
+  cluster.sync();
+  if (threadIdx.x < GN_GROUPS) {
+    float s = 0.f, q = 0.f;
+    for (int r = 0; r < CL; ++r) {
+      const float* rp = cluster.map_shared_rank(part, r);
+      s += rp[threadIdx.x * 2 + 0];
+      q += rp[threadIdx.x * 2 + 1];
+    }
+    const float cnt = (float)P * cpg;
+    const float mean = s / cnt;
+    float var = q / cnt - mean * mean;
+    var = var < 0.f ? 0.f : var;
+    const float rstd = rsqrtf(var + 1e-5f);
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rstd;
+    if (rank == 0) {
+      stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 0] = mean;
+      stats[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 1] = rstd;
+    }
+  }
+  __syncthreads();
+  cluster.barrier_arrive();                                           // our remote reads are done
+  float sa[V], sb[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = tcol * V + i, g = c / cpg;
+    sa[i] = s_rstd[g] * gamma[c];
+    sb[i] = beta[c] - s_mean[g] * sa[i];
+  }
+  sp = slab + threadIdx.x * 16;
+  char* dst = reinterpret_cast<char*>(y) + gbase + (size_t)threadIdx.x * 16;
+  const uint32_t full_groups = iters / IPC;
+  for (uint32_t k = 0; k < full_groups; ++k) {
+    uint4 v[IPC];
+#pragma unroll
+    for (int j = 0; j < IPC; ++j) v[j] = lds128(sp + j * TH * 16);
+#pragma unroll
+    for (int j = 0; j < IPC; ++j) *reinterpret_cast<uint4*>(dst + j * TH * 16) = A::apply_relu(v[j], sa, sb);
+    sp += IPC * TH * 16; dst += IPC * TH * 16;
+  }
+  for (uint32_t j = full_groups * IPC; j < iters + (threadIdx.x < rem ? 1u : 0u); ++j, sp += TH * 16, dst += TH * 16)
+    *reinterpret_cast<uint4*>(dst) = A::apply_relu(lds128(sp), sa, sb);
+  cluster.barrier_wait();                                             // every peer has read our partials: we may exit
+}
+
+// ---- backward -------------------------------------------------------------------------------------
+// DYS: dy slab resident in shared memory (second TMA load) / streamed from global (twice; the second pass hits L2).
+// NEG: generic fp32 ReLU gate (some channel has rstd*gamma <= 0); otherwise bf16 uses the packed threshold compare.
+template <typename T, int TH, bool DYS, bool NEG>
+__global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                    const T* __restrict__ addend, T* __restrict__ dx,
+                                                                    const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta,
+                                                                    const float* __restrict__ stats, int P, int C,
+                                                                    uint32_t slab_stride) {
+  using A = Acc<T>;
+  constexpr int V = A::V;
+  constexpr bool BF = sizeof(T) == 2;
+  constexpr bool PACKED = BF && !NEG;                 // packed bf16 threshold gate
+  constexpr int IPC = (int)(CHUNK / (TH * 16));
+  constexpr int U = 4;                                 // vector pairs in flight per thread per trip
+  extern __shared__ __align__(128) unsigned char smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int n = blockIdx.x / CL;
+  const uint32_t sb0 = s32(smem);
+  float* part = reinterpret_cast<float*>(smem + OFF_PART);
+  float* s_1 = reinterpret_cast<float*>(smem + OFF_SA);
+  float* s_2 = reinterpret_cast<float*>(smem + OFF_SB);
+  float* tp = reinterpret_cast<float*>(smem + gnc::HDR);
+  const uint32_t xs = sb0 + (uint32_t)(gnc::HDR + gnc::tp_bytes(TH));
+  const uint32_t ds = xs + slab_stride;
+
+  const int p0 = (int)(((long long)P * rank) / CL), p1 = (int)(((long long)P * (rank + 1)) / CL);
+  const uint32_t slab_bytes = (uint32_t)((size_t)(p1 - p0) * C * sizeof(T));
+  const size_t gbase = ((size_t)n * P + p0) * C * sizeof(T);
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < MAX_CHUNKS; ++k) { bar_init(sb0 + OFF_BAR_X + 8 * k); bar_init(sb0 + OFF_BAR_D + 8 * k); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    load_slab(xs, reinterpret_cast<const char*>(x) + gbase, slab_bytes, sb0 + OFF_BAR_X);
+    if (DYS) load_slab(ds, reinterpret_cast<const char*>(dy) + gbase, slab_bytes, sb0 + OFF_BAR_D);
+  }
+  const int cols = C / V, cpg = C / GN_GROUPS;
+  const int tcol = threadIdx.x % cols;
+  const uint32_t nvec = slab_bytes >> 4;
+  const uint32_t iters = nvec / TH, rem = nvec % TH;
+  const uint32_t n_chunks = (slab_bytes + CHUNK - 1) / CHUNK;
+  const uint32_t my_iters = iters + (threadIdx.x < rem ? 1u : 0u);
+
+  // ReLU-gate constants (live through both passes): packed bf16 thresholds, or the fp32 scale / shift
+  float sa[PACKED ? 1 : V], sbv[PACKED ? 1 : V];
+  uint32_t thr[V / 2 > 0 ? V / 2 : 1];
+  {
+    float sa_[V], sb_[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = tcol * V + i, g = c / cpg;
+      const float mean = stats[((size_t)n * GN_GROUPS + g) * 2 + 0], rstd = stats[((size_t)n * GN_GROUPS + g) * 2 + 1];
+      sa_[i] = rstd * gamma[c];
+      sb_[i] = beta[c] - mean * sa_[i];
+    }
+    if (PACKED) {
+#pragma unroll
+      for (int i = 0; i < V / 2; ++i) {
+        // sa > 0 here (NEG variant otherwise): pre > 0  <=>  x > -sb/sa
+        const uint32_t lo = floor_bf16_bits(-sb_[2 * i] / sa_[2 * i]), hi = floor_bf16_bits(-sb_[2 * i + 1] / sa_[2 * i + 1]);
+        thr[i] = lo | (hi << 16);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) { sa[PACKED ? 0 : i] = sa_[i]; sbv[PACKED ? 0 : i] = sb_[i]; }
+    }
+  }
+  __syncthreads();
+
+  // gated dy of one vector: packed (bf16 words with the dead elements zeroed) or fp32
+  auto gate = [&](const uint4& vx, const uint4& vd, float* fx, float* fd) {
+    A::unpack(vx, fx);
+    if (PACKED) {
+      uint4 m;
+      m.x = vd.x & gt2_mask(vx.x, thr[0]); m.y = vd.y & gt2_mask(vx.y, thr[1]);
+      m.z = vd.z & gt2_mask(vx.z, thr[V / 2 > 2 ? 2 : 0]); m.w = vd.w & gt2_mask(vx.w, thr[V / 2 > 3 ? 3 : 0]);
+      A::unpack(m, fd);
+    } else {
+      A::unpack(vd, fd);
+#pragma unroll
+      for (int i = 0; i < V; ++i) fd[i] = fmaf(sa[PACKED ? 0 : i], fx[i], sbv[PACKED ? 0 : i]) > 0.f ? fd[i] : 0.f;
+    }
+  };
+
+  float a[V], bq[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { a[i] = 0.f; bq[i] = 0.f; }
+  const char* dyg = reinterpret_cast<const char*>(dy) + gbase + (size_t)threadIdx.x * 16;
+  {
+    uint32_t j = 0;
+    uint32_t have = 0;                                               // chunks [0, have) have landed
+    for (; j + U <= my_iters; j += U) {
+      const uint32_t need = ((j + U) * TH * 16 + CHUNK - 1) / CHUNK;   // chunks covering iterations [j, j+U)
+      for (; have < need && have < n_chunks; ++have) { bar_wait(sb0 + OFF_BAR_X + 8 * have); if (DYS) bar_wait(sb0 + OFF_BAR_D + 8 * have); }
+      uint4 vx[U], vd[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t off = ((j + u) * TH + threadIdx.x) * 16;
+        vd[u] = DYS ? lds128(ds + off) : ldg128(dyg + (size_t)(j + u) * TH * 16);
+        vx[u] = lds128(xs + off);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float fx[V], fd[V]; gate(vx[u], vd[u], fx, fd);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { a[i] += fd[i]; bq[i] = fmaf(fd[i], fx[i], bq[i]); }
+      }
+    }
+    for (; have < n_chunks; ++have) { bar_wait(sb0 + OFF_BAR_X + 8 * have); if (DYS) bar_wait(sb0 + OFF_BAR_D + 8 * have); }
+    for (; j < my_iters; ++j) {
+      const uint32_t off = (j * TH + threadIdx.x) * 16;
+      const uint4 vd = DYS ? lds128(ds + off) : ldg128(dyg + (size_t)j * TH * 16);
+      const uint4 vx = lds128(xs + off);
+      float fx[V], fd[V]; gate(vx, vd, fx, fd);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { a[i] += fd[i]; bq[i] = fmaf(fd[i], fx[i], bq[i]); }
+    }
+  }
+  // per channel: sum dg = gamma * A ; sum dg * xhat = gamma * rstd * (B - mean * A)
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = tcol * V + i, g = c / cpg;
+    const float mean = stats[((size_t)n * GN_GROUPS + g) * 2 + 0], rstd = stats[((size_t)n * GN_GROUPS + g) * 2 + 1];
+    const float ga = gamma[c], A_ = a[i];
+    a[i] = ga * A_;
+    bq[i] = rstd * ga * (bq[i] - mean * A_);
+  }
+  group_reduce<V>(a, bq, C, tp, part);
+  cluster.sync();
+  if (threadIdx.x < GN_GROUPS) {
+    float s = 0.f, q = 0.f;
+    for (int r = 0; r < CL; ++r) {
+      const float* rp = cluster.map_shared_rank(part, r);
+      s += rp[threadIdx.x * 2 + 0];
+      q += rp[threadIdx.x * 2 + 1];
+    }
+    const float inv_m = 1.0f / ((float)P * cpg);
+    s_1[threadIdx.x] = s * inv_m;
+    s_2[threadIdx.x] = q * inv_m;
+  }
+  __syncthreads();
+  cluster.barrier_arrive();
+  // dx = rs*(dg - m1 - xhat*m2) = k1*dym + k2*x + k3
+  float k1[V], k2[V], k3[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = tcol * V + i, g = c / cpg;
+    const float mean = stats[((size_t)n * GN_GROUPS + g) * 2 + 0], rstd = stats[((size_t)n * GN_GROUPS + g) * 2 + 1];
+    const float m1 = s_1[g], m2 = s_2[g];
+    k1[i] = rstd * gamma[c];
+    k2[i] = -rstd * rstd * m2;
+    k3[i] = -rstd * m1 - k2[i] * mean;
+  }
+  char* dxg = reinterpret_cast<char*>(dx) + gbase + (size_t)threadIdx.x * 16;
+  const char* adg = addend ? reinterpret_cast<const char*>(addend) + gbase + (size_t)threadIdx.x * 16 : nullptr;
+  auto apply = [&](const uint4& vx, const uint4& vd, const uint4& va, bool has_add) -> uint4 {
+    float fx[V], fd[V], fo[V];
+    gate(vx, vd, fx, fd);
+    if (has_add) A::unpack(va, fo);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float t = fmaf(k1[i], fd[i], fmaf(k2[i], fx[i], k3[i]));
+      fo[i] = has_add ? fo[i] + t : t;
+    }
+    return A::pack(fo);
+  };
+  {
+    constexpr int U2 = 4;
+    uint32_t j = 0;
+    const bool has_add = adg != nullptr;
+    for (; j + U2 <= my_iters; j += U2) {
+      uint4 vx[U2], vd[U2], va[U2];
+#pragma unroll
+      for (int u = 0; u < U2; ++u) {
+        const uint32_t off = ((j + u) * TH + threadIdx.x) * 16;
+        vd[u] = DYS ? lds128(ds + off) : ldg128(dyg + (size_t)(j + u) * TH * 16);
+        if (has_add) va[u] = ldg128(adg + (size_t)(j + u) * TH * 16);
+        vx[u] = lds128(xs + off);
+      }
+#pragma unroll
+      for (int u = 0; u < U2; ++u)
+        *reinterpret_cast<uint4*>(dxg + (size_t)(j + u) * TH * 16) = apply(vx[u], vd[u], va[u], has_add);
+    }
+    for (; j < my_iters; ++j) {
+      const uint32_t off = (j * TH + threadIdx.x) * 16;
+      const uint4 vd = DYS ? lds128(ds + off) : ldg128(dyg + (size_t)j * TH * 16);
+      uint4 va = make_uint4(0u, 0u, 0u, 0u);
+      if (has_add) va = ldg128(adg + (size_t)j * TH * 16);
+      *reinterpret_cast<uint4*>(dxg + (size_t)j * TH * 16) = apply(lds128(xs + off), vd, va, has_add);
+    }
+  }
+  cluster.barrier_wait();
+}
+
+// any channel with rstd*gamma <= 0 needs the generic gate; gamma is constant per layer -> cached per pointer
+struct Plan { int cl, threads; bool dys; size_t smem; uint32_t stride; };
+}  // namespace gn2
+
+static int g_gn_version = -1;   // DORPATCH_GN: v2 (default), v1 (round-1 cluster kernels), twopass
+static int gn_version() {
+  if (g_gn_version < 0) {
+    const char* e = getenv("DORPATCH_GN");
+    g_gn_version = (e && strcmp(e, "v1") == 0) ? 1 : ((e && strcmp(e, "twopass") == 0) ? 0 : 2);
+  }
+  return g_gn_version;
+}
+static int gn2_env(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+static int gn2_max_cluster() {
+  static int v = -1;
+  if (v < 0) v = gn2_env("DORPATCH_GN2_MAXCL", 16);
+  return v;
+}
+// forward: smallest cluster whose slab leaves room for two CTAs per SM (256 threads), else one 512-thread CTA per SM
+static bool gn2_plan_fwd(int P, int C, size_t es, gn2::Plan* pl) {
+  static const size_t soft = (size_t)gn2_env("DORPATCH_GN2_SOFT", 111) * 1024, hard = 224 * 1024;
+  const int V = (int)(16 / es);
+  if (C % (V * 1) != 0 || (C / V) > 256 || 256 % (C / V) != 0) return false;
+  const size_t f256 = gnc::HDR + gnc::tp_bytes(256), f512 = gnc::HDR + gnc::tp_bytes(512);
+  for (int cl = 1; cl <= gn2_max_cluster(); cl *= 2) {
+    if (cl > P) break;
+    const size_t slab = (((size_t)((P + cl - 1) / cl)) * C * es + 127) / 128 * 128;
+    if (slab > gn2::MAX_CHUNKS * (size_t)gn2::CHUNK) continue;
+    if (f256 + slab <= soft) { *pl = gn2::Plan{cl, 256, false, f256 + slab, (uint32_t)slab}; return true; }
+  }
+  for (int cl = 1; cl <= gn2_max_cluster(); cl *= 2) {
+    if (cl > P) break;
+    const size_t slab = (((size_t)((P + cl - 1) / cl)) * C * es + 127) / 128 * 128;
+    if (slab > gn2::MAX_CHUNKS * (size_t)gn2::CHUNK) continue;
+    if (f512 + slab <= hard && 512 % (C / V) == 0) { *pl = gn2::Plan{cl, 512, false, f512 + slab, (uint32_t)slab}; return true; }
+  }
+  return false;
+}
+// backward: both slabs resident when they fit (two CTAs per SM, else one), else x resident + dy streamed
+static bool gn2_plan_bwd(int P, int C, size_t es, gn2::Plan* pl) {
+  static const size_t soft = (size_t)gn2_env("DORPATCH_GN2_SOFT", 111) * 1024, hard = 224 * 1024;
+  static const int dys_big = gn2_env("DORPATCH_GN2_DYS_BIG", 1);
+  const int V = (int)(16 / es);
+  if ((C / V) > 256 || 256 % (C / V) != 0) return false;
+  const size_t f256 = gnc::HDR + gnc::tp_bytes(256), f512 = gnc::HDR + gnc::tp_bytes(512);
+  for (int cl = 1; cl <= gn2_max_cluster(); cl *= 2) {
+    if (cl > P) break;
+    const size_t slab = (((size_t)((P + cl - 1) / cl)) * C * es + 127) / 128 * 128;
+    if (f256 + 2 * slab <= soft) { *pl = gn2::Plan{cl, 256, true, f256 + 2 * slab, (uint32_t)slab}; return true; }
+  }
+  if (dys_big)
+    for (int cl = 1; cl <= gn2_max_cluster(); cl *= 2) {
+      if (cl > P) break;
+      const size_t slab = (((size_t)((P + cl - 1) / cl)) * C * es + 127) / 128 * 128;
+      if (f512 + 2 * slab <= hard && 512 % (C / V) == 0) { *pl = gn2::Plan{cl, 512, true, f512 + 2 * slab, (uint32_t)slab}; return true; }
+    }
+  gn2::Plan f;
+  if (!gn2_plan_fwd(P, C, es, &f)) return false;
+  *pl = f;
+  pl->dys = false;
+  return true;
+}
+
+static bool launch_gn2_forward(const void* x, void* y, const float* gamma, const float* beta, float* stats, int N, int P,
+                               int C, bool bf16, cudaStream_t st) {
+  gn2::Plan pl;
+  if (!gn2_plan_fwd(P, C, bf16 ? 2 : 4, &pl)) return false;
+#define GN2F(TT, TH) launch_cluster(gn2::fwd_kernel<TT, TH>, pl.cl, pl.cl * N, TH, pl.smem, st, (const TT*)x, (TT*)y, gamma, beta, stats, P, C)
+  bool ok;
+  if (bf16) ok = pl.threads == 256 ? GN2F(__nv_bfloat16, 256) : GN2F(__nv_bfloat16, 512);
+  else ok = pl.threads == 256 ? GN2F(float, 256) : GN2F(float, 512);
+#undef GN2F
+  if (!ok) cudaGetLastError();
+  return ok;
+}
+
+static bool launch_gn2_backward(const void* dy, const void* x, const void* addend, void* dx, const float* gamma,
+                                const float* beta, const float* stats, int N, int P, int C, bool bf16, bool gamma_pos, cudaStream_t st) {
+  gn2::Plan pl;
+  if (!gn2_plan_bwd(P, C, bf16 ? 2 : 4, &pl)) return false;
+  const bool neg = bf16 ? !gamma_pos : true;   // fp32 always uses the fp32 gate
+#define GN2B(TT, TH, DYS, NEG) launch_cluster(gn2::bwd_kernel<TT, TH, DYS, NEG>, pl.cl, pl.cl * N, TH, pl.smem, st, (const TT*)dy, (const TT*)x, (const TT*)addend, (TT*)dx, gamma, beta, stats, P, C, pl.stride)
+#define GN2B_T(TT, NEG) (pl.threads == 256 ? (pl.dys ? GN2B(TT, 256, true, NEG) : GN2B(TT, 256, false, NEG)) : (pl.dys ? GN2B(TT, 512, true, NEG) : GN2B(TT, 512, false, NEG)))
+  bool ok;
+  if (bf16) ok = neg ? GN2B_T(__nv_bfloat16, true) : GN2B_T(__nv_bfloat16, false);
+  else ok = GN2B_T(float, true);
+#undef GN2B_T
+#undef GN2B
+  if (!ok) cudaGetLastError();
+  return ok;
+}
+
 void launch_gn_relu_forward(const void* x, void* y, const float* gamma, const float* beta, float* partial,
                             float* stats, int N, int P, int C, bool bf16, cudaStream_t st) {
+  if (gn_version() == 2 && launch_gn2_forward(x, y, gamma, beta, stats, N, P, C, bf16, st)) return;
   GnPlan pl;
-  if (gn_plan(P, C, bf16 ? 2 : 4, &pl)) {
+  if (gn_version() >= 1 && gn_plan(P, C, bf16 ? 2 : 4, &pl)) {
     const int grid = gn_grid(pl, N);
     bool ok;
     if (bf16) ok = launch_cluster(gn_fwd_cluster_kernel<__nv_bfloat16>, pl.cl, grid, pl.threads, pl.smem, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, gamma, beta, stats, N, P, C, gn_nbuf(pl), pl.slab_stride);
@@ -1168,10 +1684,11 @@ void launch_gn_relu_forward(const void* x, void* y, const float* gamma, const fl
 
 void launch_gn_relu_backward(const void* dy, const void* x, const void* addend, void* dx, const float* gamma,
                              const float* beta, const float* stats, float* partial, int N, int P, int C, bool bf16,
-                             cudaStream_t st) {
+                             cudaStream_t st, bool gamma_pos) {
+  if (gn_version() == 2 && launch_gn2_backward(dy, x, addend, dx, gamma, beta, stats, N, P, C, bf16, gamma_pos, st)) return;
   GnPlan pl;
   const bool ug = (C / GN_GROUPS) >= (bf16 ? 8 : 4);
-  {   // both slabs in shared memory when they fit (DORPATCH_GN_DYSMEM=0 disables)
+  if (gn_version() >= 1) {   // both slabs in shared memory when they fit (DORPATCH_GN_DYSMEM=0 disables)
     static int dys = -1;
     if (dys < 0) { const char* e = getenv("DORPATCH_GN_DYSMEM"); dys = e ? atoi(e) : 1; }
     const size_t es = bf16 ? 2 : 4, fixed = gnc::HDR + gnc::tp_bytes(gnc::THREADS);
@@ -1192,7 +1709,7 @@ void launch_gn_relu_backward(const void* dy, const void* x, const void* addend, 
       }
     }
   }
-  if (gn_plan(P, C, bf16 ? 2 : 4, &pl)) {
+  if (gn_version() >= 1 && gn_plan(P, C, bf16 ? 2 : 4, &pl)) {
     const int grid = gn_grid(pl, N);
     bool ok;
 #define GNB(TT, UGV) launch_cluster(gn_bwd_cluster_kernel<TT, UGV>, pl.cl, grid, pl.threads, pl.smem, st, (const TT*)dy, (const TT*)x, (const TT*)addend, (TT*)dx, gamma, beta, stats, N, P, C, gn_nbuf(pl), pl.slab_stride)

@@ -297,52 +297,61 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
   // (global visibility of the bulk stores is guaranteed at kernel completion)
 }
 
+// Launch shape.  Work items = images x row tiles (R rows) x sample groups, walked grid-stride by the resident CTAs.
+// The item count of ONE classifier chunk is small (16 images x 28 tiles = 448 at R = 8) and a CTA's cost is dominated
+// by its items' stores, so the grid is chosen for wave efficiency: over the tile heights that divide H and the
+// power-of-two sample-group counts, maximise items / (waves x resident CTAs), residency taken from the occupancy
+// API (round 1 sized the grid from shared memory alone: 448 items on 444 slots = a second wave for 4 CTAs,
+// 0.50 of HBM peak in-step against 0.69 stand-alone).  DORPATCH_K1_ROWS / _K1_SG pin the choice.
 template <typename T, int CP, bool FUSED>
 static void expand_launch(const ExpandParams& p, int num_sms, cudaStream_t st) {
-  static int rows_env = -1;
-  if (rows_env < 0) { const char* e = getenv("DORPATCH_K1_ROWS"); rows_env = e ? atoi(e) : EXP_R_DEFAULT; if (rows_env < 1) rows_env = EXP_R_DEFAULT; }
-  int EXP_R = rows_env;
-  while (EXP_R > 1 && (p.H % EXP_R != 0 || (size_t)EXP_R * p.W * ((FUSED ? 7 : 3) * 4 + CP * sizeof(T)) > 200 * 1024)) EXP_R /= 2;
-  const size_t smem = EXP_HDR + (size_t)(FUSED ? 7 : 3) * EXP_R * p.W * 4 + (size_t)EXP_R * p.W * CP * sizeof(T);
+  static int rows_env = -2, sg_env = -1;
+  if (rows_env == -2) {
+    const char* e = getenv("DORPATCH_K1_ROWS"); rows_env = e ? atoi(e) : 0;
+    const char* g = getenv("DORPATCH_K1_SG"); sg_env = g ? atoi(g) : 0;
+  }
+  constexpr int NP = FUSED ? 7 : 3;
+  auto smem_of = [&](int R) { return (size_t)EXP_HDR + (size_t)NP * R * p.W * 4 + (size_t)R * p.W * CP * sizeof(T); };
+  static int occ_cache[33];
+  static bool occ_init = false;
+  if (!occ_init) { for (int& v : occ_cache) v = -1; occ_init = true; }
+  auto resident = [&](int R) {
+    if (occ_cache[R] < 0) {
+      const size_t sm = smem_of(R);
+      cudaFuncSetAttribute(expand_kernel<T, CP, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, expand_kernel<T, CP, FUSED>, EXP_THREADS, sm) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
+      occ_cache[R] = nb;
+    }
+    return occ_cache[R];
+  };
+  const int nb_img = (p.n0 + p.n - 1) / p.S - p.n0 / p.S + 1;
+  int best_R = 0, best_sg = 1, best_grid = 1;
+  double best_score = -1.0;
+  const int cand[] = {16, 14, 8, 7, 4, 2, 1};
+  for (int R : cand) {
+    if (rows_env > 0 && R != rows_env) continue;
+    if (R > 32 || p.H % R != 0 || smem_of(R) > 200 * 1024) continue;
+    const int slots = num_sms * resident(R);
+    const int tiles = p.H / R;
+    for (int sg = 1; sg <= 32 && (sg == 1 || sg * EXP_WARPS <= p.S); sg *= 2) {
+      if (sg_env > 0 && sg != sg_env) continue;
+      const int items = nb_img * tiles * sg;
+      const int waves = (items + slots - 1) / slots;
+      double score = (double)items / ((double)waves * slots);
+      // each sample group re-loads and re-composes the tile; small tiles pay the per-item setup more often
+      for (int q = sg; q > 1; q >>= 1) score *= 0.97;
+      if (R < 7) score *= 0.94;
+      if (score > best_score) { best_score = score; best_R = R; best_sg = sg; best_grid = items < slots ? items : slots; }
+    }
+  }
+  if (best_R == 0) { best_R = 1; best_sg = 1; best_grid = nb_img * p.H; }
+  const size_t smem = smem_of(best_R);
   cudaFuncSetAttribute(expand_kernel<T, CP, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ExpandParams q = p;
-  q.R = EXP_R;
-  const int nb = (p.n0 + p.n - 1) / p.S - p.n0 / p.S + 1;
-  const int tiles = p.H / EXP_R;
-  static int ctas_env = -1;
-  if (ctas_env < 0) { const char* e = getenv("DORPATCH_K1_CTAS"); ctas_env = e ? atoi(e) : 0; }
-  int ctas_per_sm = (int)((200 * 1024) / smem);
-  if (ctas_env > 0) ctas_per_sm = ctas_env;                 // experiment knob: resident CTAs per SM assumed by the grid
-  if (ctas_per_sm < 1) ctas_per_sm = 1;
-  if (ctas_per_sm > 6) ctas_per_sm = 6;
-  const int target = num_sms * ctas_per_sm;
-  // Work split: items = images x row tiles x sample groups, walked grid-stride by as many CTAs as are resident.
-  // DORPATCH_K1_BALANCE=1 instead sizes the grid to items / waves so that every CTA gets the same item count
-  // (measured on B200 at 32 x 16 samples: 0.060-0.070 ms against 0.056 ms -- fewer resident CTAs cost more than
-  // the ragged last wave), DORPATCH_K1_SG forces the sample-group count under that policy.
-  static int sg_env = -1, balance = 0;
-  if (sg_env < 0) {
-    const char* e = getenv("DORPATCH_K1_SG"); sg_env = e ? atoi(e) : 0;
-    if (const char* b = getenv("DORPATCH_K1_BALANCE")) balance = atoi(b);
-  }
-  int sg = 1, grid = 1;
-  if (!balance) {                                   // fill the machine, ragged last wave
-    while (nb * tiles * sg < target && sg * EXP_WARPS < p.S && sg < 32) sg *= 2;
-    grid = nb * tiles * sg;
-    if (grid > target) grid = target;
-  } else {
-    int best_grid = 0;
-    for (int c = 1; c <= 32 && (c == 1 || c * EXP_WARPS <= p.S); c *= 2) {
-      if (sg_env > 0 && c != sg_env) continue;
-      const int items = nb * tiles * c;
-      const int waves = (items + target - 1) / target;
-      const int g = (items + waves - 1) / waves;
-      if (g > best_grid + best_grid / 16) { best_grid = g; sg = c; grid = g; }   // prefer fewer groups unless >6 % more CTAs
-    }
-    if (best_grid == 0) { sg = 1; const int items = nb * tiles; const int waves = (items + target - 1) / target; grid = (items + waves - 1) / waves; }
-  }
-  q.sgroups = sg;
-  expand_kernel<T, CP, FUSED><<<grid, EXP_THREADS, smem, st>>>(q);
+  q.R = best_R;
+  q.sgroups = best_sg;
+  expand_kernel<T, CP, FUSED><<<best_grid, EXP_THREADS, smem, st>>>(q);
 }
 
 void launch_expand(const float* img, const float* x, const float* mask, const float* pattern, const float* scale,

@@ -53,14 +53,37 @@ parser.add_argument('--img_size', default=224, type=int, help='synthetic image s
 parser.add_argument('--seed', default=0, type=int, help='seed of the random-init weights')
 
 
+def _init_distributed():
+    """Under torchrun (RANK / WORLD_SIZE / LOCAL_RANK set): one process per GPU, NCCL process group, the EOT axis of
+    every generate() call sharded over the ranks (attack._dist).  Returns (rank, world)."""
+    if "RANK" not in os.environ or int(os.environ.get("WORLD_SIZE", "1")) < 2:
+        return 0, 1
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank(), dist.get_world_size()
+
+
 def main(args):
-    set_device(args.device)
+    rank, world = 0, 1
+    if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        rank, world = _init_distributed()        # the launcher assigned the GPU: --device is not applied
+    else:
+        set_device(args.device)
     set_random_seed()
     if args.precision:
         os.environ["DORPATCH_PRECISION"] = args.precision
     if args.chunk:
         os.environ["DORPATCH_CHUNK"] = str(args.chunk)
     result_dir = generate_saving_path(vars(args).copy())
+    if world > 1:
+        import torch.distributed as dist
+
+    def sync_ranks():
+        if world > 1:
+            dist.barrier()
 
     model = get_model(args.dataset, args.base_arch, args.model_dir, random_init=args.random_init, seed=args.seed)
     model = NormModel(model, get_normalize(args.dataset, args.base_arch))
@@ -112,8 +135,10 @@ def main(args):
                     y=target if args.targeted else None, lr=args.lr, num_patch=args.num_patch, dropout=args.dropout,
                     density=args.density, structured=args.structured, save_dir=result_dir, batch_id=i,
                     eps=args.epsilon, max_iterations=args.max_iterations, sampling_size=args.sampling_size)
-                torch.save(adv_mask, os.path.join(result_dir, "adv_mask_%d.pt" % i))
-                torch.save(adv_pattern, os.path.join(result_dir, "adv_pattern_%d.pt" % i))
+                if rank == 0:                     # every rank holds the identical result; one writer
+                    torch.save(adv_mask, os.path.join(result_dir, "adv_mask_%d.pt" % i))
+                    torch.save(adv_pattern, os.path.join(result_dir, "adv_pattern_%d.pt" % i))
+                sync_ranks()
 
             adv_x, _, _ = eng.paste(x, adv_mask, adv_pattern, args.epsilon)
 
@@ -123,8 +148,10 @@ def main(args):
                     records_batch = pickle.load(f)
             else:
                 records_batch = [[d.robust_predict(im, True) for d in defense] for im in adv_x]
-                with open(pc_path, 'wb') as f:
-                    pickle.dump(records_batch, f)
+                if rank == 0:
+                    with open(pc_path, 'wb') as f:
+                        pickle.dump(records_batch, f)
+                sync_ranks()
 
             preds_list.append(preds.cpu().numpy())
             y_list.append(y.cpu().numpy())
@@ -151,7 +178,8 @@ def main(args):
     line = "clean accuracy: {:.2f}%, robust accuracy:{:.2f}%, acc@PC:{:s}%, certified_ACC@PC:{:s}%, certified_ASR@PC:{:s}%".format(
         acc_clean, acc_robust, convert_float_list_to_str(acc_PC), convert_float_list_to_str(certified_acc_PC),
         convert_float_list_to_str(certified_asr_PC))
-    print(line)
+    if rank == 0:
+        print(line)
     return dict(acc_clean=acc_clean, acc_robust=acc_robust, acc_PC=acc_PC, certified_acc_PC=certified_acc_PC,
                 certified_asr_PC=certified_asr_PC, result_dir=result_dir, line=line)
 

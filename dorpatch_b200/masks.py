@@ -78,3 +78,55 @@ def to_bool(table, img_size):
         for r0, r1, c0, c1 in table[k].reshape(-1, 4):
             m[k, 0, r0:r1, c0:c1] = False
     return m
+
+
+def from_bool(masks):
+    """Inverse of to_bool for API compatibility: bool keep-masks [n,1,H,W] (torch or numpy) -> rectangle table
+    [n,2,4] int16.  Each mask's occluded set must be a union of <= 2 axis-aligned rectangles, as the reference
+    builds them (PatchCleanser.py:51-58: one rectangle per single mask, the union of two per double mask); anything
+    else raises -- the engine has no dense-mask path."""
+    m = masks.detach().cpu().numpy() if hasattr(masks, "detach") else np.asarray(masks)
+    m = m.reshape(m.shape[0], m.shape[-2], m.shape[-1]).astype(bool)
+    out = np.zeros((m.shape[0], 2, 4), np.int16)
+    for k in range(m.shape[0]):
+        out[k] = _decompose(~m[k], k)
+    return out
+
+
+def _decompose(occ, k=0):
+    """occ (bool [H,W]) as a union of <= 2 rectangles.  Work on the coarse grid of rows / columns where the pattern
+    changes (<= 5 x 5 cells): the first rectangle starts at the first occluded cell; try each of its extents, the
+    second rectangle is then the bounding box of what is left, valid if it lies inside the occluded set."""
+    H, W = occ.shape
+    out = np.zeros((2, 4), np.int16)
+    if not occ.any():
+        return out
+    rb = [0] + [i for i in range(1, H) if not np.array_equal(occ[i], occ[i - 1])] + [H]
+    cb = [0] + [j for j in range(1, W) if not np.array_equal(occ[:, j], occ[:, j - 1])] + [W]
+    g = occ[np.ix_(rb[:-1], cb[:-1])]
+    a0 = int(np.argmax(g.any(1)))
+    b0 = int(np.argmax(g[a0]))
+    for a1 in range(a0 + 1, g.shape[0] + 1):
+        for b1 in range(b0 + 1, g.shape[1] + 1):
+            if not g[a0:a1, b0:b1].all():
+                continue
+            rest = g.copy()
+            rest[a0:a1, b0:b1] = False
+            if not rest.any():
+                out[0] = (rb[a0], rb[a1], cb[b0], cb[b1])
+                return out
+            rr, cc = np.nonzero(rest)
+            # the second rectangle may overlap the first: grow the remainder's bounding box over occluded cells
+            for c0 in range(int(rr.min()), -1, -1):
+                for d0 in range(int(cc.min()), -1, -1):
+                    c1, d1 = int(rr.max()) + 1, int(cc.max()) + 1
+                    if not g[c0:c1, d0:d1].all():
+                        continue
+                    u = np.zeros_like(g)
+                    u[a0:a1, b0:b1] = True
+                    u[c0:c1, d0:d1] = True
+                    if np.array_equal(u, g):
+                        out[0] = (rb[a0], rb[a1], cb[b0], cb[b1])
+                        out[1] = (rb[c0], rb[c1], cb[d0], cb[d1])
+                        return out
+    raise NotImplementedError("mask %d is not a union of <= 2 axis-aligned rectangles" % k)

@@ -19,7 +19,7 @@ def shared_engine(img, max_images=1):
         if e.handle and e.img == img and e.device == dev and e.max_images >= max_images:
             return e
     from .engine import Engine
-    e = Engine(img=img, precision=os.environ.get("DORPATCH_PRECISION", "bf16"), chunk=1,
+    e = Engine(img=img, precision=os.environ.get("DORPATCH_PRECISION", "tf32"), chunk=1,
                max_images=max(1, int(max_images)), autotune=False)
     _ENGINES.append(e)
     return e

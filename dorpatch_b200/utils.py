@@ -35,9 +35,19 @@ EXTRA_FLAGS = ("synthetic", "random_init", "max_iterations", "sampling_size", "n
                "precision", "chunk", "img_size", "seed")
 
 
+# extra flags that change WHAT is computed (and therefore the artefacts a later run would resume from), with the
+# value at which the run is the reference's: any other value is appended to the first path component, so a
+# synthetic / random-init / truncated run can never be resumed as (or shadow) a real one.  precision / chunk /
+# num_batches do not change the artefacts' meaning and stay out of the path.
+ARTEFACT_FLAGS = (("synthetic", 0), ("random_init", False), ("max_iterations", 5000), ("sampling_size", 128),
+                  ("img_size", 224), ("seed", 0))
+
+
 def generate_saving_path(configs):
-    """results/<k=v joined by _>/num_patch=.._patch_budget=..  (utils.py:24-44)."""
+    """results/<k=v joined by _>/num_patch=.._patch_budget=..  (utils.py:24-44).  With the reference's flag values the
+    path is the reference's; non-default values of the flags in ARTEFACT_FLAGS add a `__k=v_...` suffix."""
     json.dumps(configs, indent=4)
+    extra = ["%s=%s" % (k, configs[k]) for k, d in ARTEFACT_FLAGS if k in configs and configs[k] != d]
     for k in ["device", "model_dir", "data_dir", "batch_size", "lr", "epsilon"] + list(EXTRA_FLAGS):
         configs.pop(k, None)
     subdir = ''
@@ -47,7 +57,10 @@ def generate_saving_path(configs):
             parts.append("%s=%s" % (k, configs.pop(k)))
         subdir = '_'.join(parts)
     print(subdir)
-    save_path = os.path.join("results", "_".join("%s=%s" % (k, v) for k, v in configs.items()), subdir)
+    top = "_".join("%s=%s" % (k, v) for k, v in configs.items())
+    if extra:
+        top += "__" + "_".join(extra)
+    save_path = os.path.join("results", top, subdir)
     os.makedirs(save_path, exist_ok=True)
     return save_path
 
@@ -163,8 +176,10 @@ def clip(mask, pattern, x, eps):
         raise RuntimeError("dorpatch_b200.utils.clip runs on the native CUDA engine only (no CPU fallback)")
     from .runtime import shared_engine
     eng = shared_engine(x.shape[-1], x.shape[0])
-    adv, _, _ = eng.paste(x.contiguous().float(), mask.contiguous().float(), pattern.contiguous().float(), eps)
-    return adv - x
+    x, mask, pattern = x.contiguous().float(), mask.contiguous().float(), pattern.contiguous().float()
+    _, _, scale = eng.paste(x, mask, pattern, eps)       # the native kernel's min(eps / ||delta||_2, 1) per image
+    # delta itself (utils.py:107-110), not (x + delta) - x: the latter loses delta's low bits to cancellation
+    return mask * (pattern - x) * torch.from_numpy(scale).to(x.device).view(-1, 1, 1, 1)
 
 
 def convert_float_list_to_str(l):

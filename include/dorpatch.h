@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DP_ABI_VERSION 4
+#define DP_ABI_VERSION 5
 
 enum dp_precision {
   DP_PREC_FP32 = 0, /* fp32 storage, fp32 FMA math (no tensor cores): parity checks   */
@@ -106,6 +106,12 @@ int32_t dp_expand(dp_engine* e, const float* img, int32_t B, int32_t S, const in
  * synchronisation -- exactly one kernel launch on `stream` (what bench.py brackets with CUDA events). */
 int32_t dp_expand_dev(dp_engine* e, const float* img, int32_t B, int32_t S, const int16_t* rects_dev,
                       void* out, void* stream);
+/* The variant of K1 the hot loop launches (attack.py:184-185 fused in: reads x / mask / pattern [B,...] dev and the
+ * clip scale of the last dp_paste / dp_attack_grad on these tensors), for samples [n0, n0+n) of the b-major
+ * [B*S] ordering -- one classifier chunk.  Rectangles on the device; exactly one kernel launch, no synchronisation
+ * (bench.py's roofline leg times this launch). */
+int32_t dp_expand_step_dev(dp_engine* e, const float* x, const float* mask, const float* pattern, int32_t B, int32_t S,
+                           const int16_t* rects_dev, int32_t n0, int32_t n, void* out, void* stream);
 int32_t dp_input_layout(const dp_engine* e, int32_t* c_pad, int32_t* elem_bytes);
 
 /* ---- forward-only: model(occlude(img)) ---------------------------------------------- */
@@ -181,6 +187,21 @@ int32_t dp_attack_step_host(dp_engine* e, const dp_attack_args* g, const dp_upda
  * fp32 dev; if dlogits_dev != NULL also writes dz_dev [N,3,H,W] fp32 (d/dz). */
 int32_t dp_net_forward_backward(dp_engine* e, const float* z, int32_t N, float* logits_dev,
                                 const float* dlogits_dev, float* dz_dev, void* stream);
+
+/* Op-level hooks for the parity tests (tests/test_gpu_ops.py); not part of the reference-facing surface.
+ * dp_debug_stem_bwd_reduce: the bf16 engine's fused stem-dgrad + masked EOT reduce (K1^T as the bench runs it) on a
+ *   caller-supplied dY [B*S, H/2, H/2, 64] bf16 dev: G[B,3,H,W] = 2 * sum_s keep_s * conv7x7s2^T(dY_s, W_stem).
+ * dp_debug_gn_gemm: the tcgen05 GroupNorm-prologue GEMM on caller-supplied operands: out[m,n] = sum_k
+ *   relu(gn(x))[m,k] * W[n,k] (+ shortcut); x [N*P,K] bf16, w_nk [Nout,K] bf16, stats [N,32,2] (mean, rstd), all dev.
+ * dp_debug_gn: GroupNorm(32)+ReLU forward (and, with dy, backward-to-input) in the engine's activation dtype on
+ *   caller-supplied [N,P,C] tensors; stats [N,32,2] dev out. */
+int32_t dp_debug_stem_bwd_reduce(dp_engine* e, const void* dY, const int16_t* rects_host, int32_t B, int32_t S, float* G,
+                                 void* stream);
+int32_t dp_debug_gn_gemm(dp_engine* e, const void* x, const void* w_nk, const float* stats, const float* gamma,
+                         const float* beta, const void* shortcut, void* out, int32_t N, int32_t P, int32_t K,
+                         int32_t Nout, void* stream);
+int32_t dp_debug_gn(dp_engine* e, const void* x, const void* dy, const void* addend, const float* gamma, const float* beta,
+                    int32_t gamma_positive, void* y, void* dx, float* stats, int32_t N, int32_t P, int32_t C, void* stream);
 
 #ifdef __cplusplus
 }

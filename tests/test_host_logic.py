@@ -120,9 +120,13 @@ def test_result_path_and_cli_surface(tmp_path, monkeypatch):
     args = M.parser.parse_args(["--targeted", "--dropout", "1", "--synthetic", "3", "--max_iterations", "7"])
     assert (args.batch_size, args.epsilon, args.lr, args.patch_budget, args.num_patch) == (1, 4.0, 0.01, 0.12, -1)
     p = generate_saving_path(vars(args).copy())
-    assert p == ("results/dataset=imagenet_base_arch=resnetv2_targeted=True_attack=DorPatch_dropout=1_"
-                 "density=0.001_structured=0.001/num_patch=-1_patch_budget=0.12")
+    ref_top = "results/dataset=imagenet_base_arch=resnetv2_targeted=True_attack=DorPatch_dropout=1_density=0.001_structured=0.001"
+    # flags that change the artefacts (synthetic data, truncated run) may not share the real run's directory
+    assert p == ref_top + "__synthetic=3_max_iterations=7/num_patch=-1_patch_budget=0.12"
     assert os.path.isdir(p)
+    # with the reference's own flag values the path is the reference's (utils.py:24-44), whatever precision / chunk say
+    args = M.parser.parse_args(["--targeted", "--dropout", "1", "--precision", "bf16", "--chunk", "64", "--num_batches", "3"])
+    assert generate_saving_path(vars(args).copy()) == ref_top + "/num_patch=-1_patch_budget=0.12"
     ref_flags = ["--device", "--dataset", "--data_dir", "--model_dir", "--base_arch", "--targeted", "--patch_budget",
                  "--attack", "--batch-size", "--epsilon", "--lr", "--num_patch", "--dropout", "--density", "--structured"]
     have = {o for a in M.parser._actions for o in a.option_strings}
@@ -141,3 +145,21 @@ def test_reference_module_names_resolve():
     rec = PatchCleanserRecord(3, True, np.arange(36), np.ones(630, bool))
     back = pickle.loads(pickle.dumps([[rec]]))
     assert back[0][0].prediction == 3 and back[0][0].preds_2.shape == (630,)
+
+
+def test_bool_universe_round_trips_to_rectangles():
+    """collect_failure's reference signature takes the bool mask universe (attack.py:384-406); the native path needs
+    rectangles: masks.from_bool must invert masks.to_bool on the whole universe, and reject anything else."""
+    from dorpatch_b200 import masks as PM
+    for dropout in (1, 2):
+        table = PM.universe(112, dropout)
+        dense = PM.to_bool(table, 112)
+        sel = np.arange(len(table)) if dropout == 1 else np.random.RandomState(0).choice(len(table), 300, replace=False)
+        back = PM.from_bool(dense[sel])
+        assert np.array_equal(PM.to_bool(back, 112), dense[sel])
+    bad = np.ones((1, 1, 112, 112), bool)
+    bad[0, 0, 3:9, 3:9] = False
+    bad[0, 0, 20:30, 40:50] = False
+    bad[0, 0, 60:70, 5:15] = False                # three rectangles: no dense-mask path exists
+    with pytest.raises(NotImplementedError):
+        PM.from_bool(bad)
