@@ -207,6 +207,7 @@ class Workload:
         self.y, self.crit = y, [bool(c["targeted"])] * B
         self.states = [_ImageState(0.01, 1e-3, y[b], c["targeted"], np.random.RandomState(1234 + b)) for b in range(B)]
         self.PM = PM
+        self.nff0, self.act1 = np.zeros(B, np.int32), np.ones(B, np.uint8)
         self.hx = torch.empty(self.x.shape, pin_memory=True).copy_(self.x)
         self.hm = torch.empty(self.mask.shape, pin_memory=True).copy_(self.mask)
         self.hp = torch.empty(self.pattern.shape, pin_memory=True).copy_(self.pattern)
@@ -230,8 +231,10 @@ class Workload:
         target = r["group_lasso"] if self.stage == 0 else r["loss_struc"]
         st_used = [s.structured for s in self.states]
         cg_used = [s.coeff_group_lasso for s in self.states]
+        # failed-mask sets live on the device (as in DorPatch.generate): one kernel, the host reads the set sizes
+        counts = self.eng.failed_update(idx, self.nff0, self.act1, loss=loss_adv if self.world > 1 else None)
         for b, s in enumerate(self.states):
-            s.bookkeeping(self.stage, i, loss_adv[b], idx[b], 0, target[b])
+            s.bookkeeping(self.stage, i, loss_adv[b], idx[b], 0, target[b], n_failed=counts[b])
         return np.full(self.B, 0.01, np.float32), st_used, cg_used
 
     def step(self, i):
@@ -250,8 +253,9 @@ class Workload:
             r = self.eng.attack_step_host(self.hx.numpy(), self.hm.numpy(), self.hp.numpy(), rects, self.y, self.crit, 0.1, 4.0,
                                           self.stage, lr, st_used, cg_used, 1e-3, S_total=self.S)
             target = r["group_lasso"] if self.stage == 0 else r["loss_struc"]
+            counts = self.eng.failed_update(idx, self.nff0, self.act1)
             for b, s in enumerate(self.states):
-                s.bookkeeping(self.stage, i, r["loss_adv"][b], idx[b], 0, target[b])
+                s.bookkeeping(self.stage, i, r["loss_adv"][b], idx[b], 0, target[b], n_failed=counts[b])
         else:
             self.dx.copy_(self.hx, non_blocking=True); self.dm.copy_(self.hm, non_blocking=True); self.dp_.copy_(self.hp, non_blocking=True)
             r = self.eng.attack_grad(self.dx, self.dm, self.dp_, rects, self.y, self.crit, 0.1, 4.0, self.stage, self.G, S_total=self.S)

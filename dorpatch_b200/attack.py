@@ -81,10 +81,18 @@ class _ImageState(object):
         self.y = int(y)
         self.targeted = bool(targeted)           # the `targeted` variable (scan semantics)
         self.crit_targeted = bool(targeted)      # self.criterion.targeted
-        self.failed = []
+        self.failed = []                         # host copy of the failed-mask set (authoritative only when dev is None)
+        self.n_failed = 0
+        self.dev = None                          # (engine, image slot): the set lives on the device as a bitmap (N2)
         self.certifiable = False
         self.rng = rng
         self.reset()
+
+    def set_failed(self, indices):               # a universe scan replaced the set (attack.py:187-190)
+        self.failed = list(indices)
+        self.n_failed = len(self.failed)
+        if self.dev is not None:
+            self.dev[0].failed_write(self.dev[1], self.failed)
 
     def reset(self):                             # attack.py:129-132
         self.lr = np.float32(self.lr0)
@@ -94,23 +102,29 @@ class _ImageState(object):
         self.active = True
 
     def sample(self, i, n_mask, S):              # attack.py:193-204
-        n_ff = 0 if i < 1000 else min(len(self.failed), S // 2)
+        n_ff = 0 if i < 1000 else min(self.n_failed, S // 2)
         parts = []
         if n_ff > 0:
+            if self.dev is not None:             # the only reader of the set's CONTENT: fetch the sorted indices
+                self.failed = self.dev[0].failed_read(self.dev[1])
             parts.append(self.rng.choice(self.failed, n_ff, replace=False))
         if S - n_ff > 0:
             parts.append(self.rng.choice(np.arange(n_mask), S - n_ff, replace=False))
         return np.concatenate(parts), n_ff
 
-    def bookkeeping(self, stage, i, loss_adv, idx, n_ff, loss_target):   # attack.py:249-308
+    def bookkeeping(self, stage, i, loss_adv, idx, n_ff, loss_target, n_failed=None):   # attack.py:249-308
+        """n_failed: size of the failed set after this step when the device keeps it (dp_failed_set_update);
+        None = update the host list here (attack.py:259-267)."""
         ok = loss_adv < np.float32(1e-1)
-        gone = idx[:n_ff][ok[:n_ff]]
-        if len(gone) > 0:
-            self.failed = np.setdiff1d(self.failed, gone).tolist()
-        new = idx[n_ff:][~ok[n_ff:]]
-        if len(new) > 0:
-            self.failed = np.unique(list(self.failed) + list(new)).tolist()
-        n_failed = len(self.failed)
+        if n_failed is None:
+            gone = idx[:n_ff][ok[:n_ff]]
+            if len(gone) > 0:
+                self.failed = np.setdiff1d(self.failed, gone).tolist()
+            new = idx[n_ff:][~ok[n_ff:]]
+            if len(new) > 0:
+                self.failed = np.unique(list(self.failed) + list(new)).tolist()
+            n_failed = len(self.failed)
+        self.n_failed = int(n_failed)
         self.certifiable = n_failed == 0
         if n_failed < self.num_failure:
             self.loss_best = np.float32(np.inf)
@@ -273,6 +287,11 @@ class DorPatch(object):
         else:
             rngs = [np.random.RandomState(int(np.random.randint(0, 2 ** 31 - 1))) for _ in range(B)]
         st = [_ImageState(lr, structured, y[b], targeted, rngs[b]) for b in range(B)]
+        device_sets = os.environ.get("DORPATCH_FAILED", "device") != "host" and n_mask <= 4096
+        if device_sets:                                          # failed-mask sets as device bitmaps
+            for b, s in enumerate(st):
+                s.dev = (eng, b)
+                s.set_failed([])
         dir_0 = os.path.dirname(save_dir.rstrip('/')) if save_dir else None
         G = torch.zeros_like(x)
         use_eot = (eot_affine != 0.0) or (eot_colour != 0.0)
@@ -333,14 +352,14 @@ class DorPatch(object):
                             print(">> switch to targeted attack to category {:3d} at iteration: {:4d}".format(s.y, i))
                         s.crit_targeted = s.crit_targeted or sw
                         s.reset()
-                        s.failed = scan(b, adv_x_prev)
+                        s.set_failed(scan(b, adv_x_prev))
                 if stage == 0 and i == 499 and any(s.active and not s.targeted for s in st):
                     adv_x_prev, _, _ = eng.paste(x, adv_mask, adv_pattern, eps)   # the `adv_x` step 500 scans
                 if i % 100 == 0:                                 # attack.py:187-190
                     adv_x, _, _ = eng.paste(x, adv_mask, adv_pattern, eps)
                     for b, s in enumerate(st):
                         if s.active:
-                            s.failed = scan(b, adv_x)
+                            s.set_failed(scan(b, adv_x))
                 idx = np.zeros((B, S), np.int64)
                 idx2 = np.zeros((B, S), np.int64) if dual else None
                 nff = [0] * B
@@ -364,12 +383,16 @@ class DorPatch(object):
                     loss_adv, preds = exchange_shards(dist, G, loss_adv, preds)
                 last_preds = preds
                 loss_target = r["group_lasso"] if stage == 0 else r["loss_struc"]
+                counts = None
+                if device_sets:                                  # attack.py:259-267 as one kernel over the bitmaps; the host reads set sizes only
+                    counts = eng.failed_update(idx, nff, [s.active for s in st], loss=loss_adv if dist else None)
                 lr_used = np.zeros(B, np.float32)
                 stopped_now = []
                 for b, s in enumerate(st):
                     if not s.active:
                         continue
-                    improved, stop = s.bookkeeping(stage, i, loss_adv[b], idx[b], nff[b], loss_target[b])
+                    improved, stop = s.bookkeeping(stage, i, loss_adv[b], idx[b], nff[b], loss_target[b],
+                                                   n_failed=None if counts is None else counts[b])
                     if stop:
                         stopped_now.append(b)
                     if improved:                                 # best snapshot stays on the device

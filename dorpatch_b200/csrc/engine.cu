@@ -172,6 +172,10 @@ struct dp_engine {
   float* adv_x = nullptr; float* dLs = nullptr; float* scale = nullptr; float* l2 = nullptr;
   float* loss_struc = nullptr; float* loss_density = nullptr; float* group_lasso = nullptr;
   float* win_dev = nullptr; float* grp_ss = nullptr;
+  // failed-mask sets (N2): one bitmap of FAILED_WORDS words per image, its popcounts, staging for one step's indices
+  static constexpr int FAILED_WORDS = 128;        // up to 4096 masks (the reference's universe has 2520)
+  uint32_t* failed_bits = nullptr; int32_t* failed_count = nullptr; int32_t* failed_idx = nullptr; int32_t* failed_nff = nullptr;
+  uint8_t* failed_active = nullptr; float* failed_loss = nullptr; int failed_cap = 0;
   float* helper_scale = nullptr; float* helper_l2 = nullptr; float* helper_ws = nullptr;   // scratch of dp_paste(out) / dp_window_sum
   float* lr_d = nullptr; float* structured_d = nullptr; float* coeff_d = nullptr;
   float* host_x = nullptr; float* host_mask = nullptr; float* host_pattern = nullptr; float* host_G = nullptr;  // dp_attack_step_host
@@ -220,6 +224,21 @@ struct dp_engine {
     prof_recs.clear();
   }
 
+  // ---- whole-step CUDA graphs: dp_attack_grad's launch sequence (staging copies, paste, regularisers,
+  // every chunk's K1 -> forward -> CW -> backward -> K1^T on both lanes, result copies) captured once per call
+  // signature and replayed; the first call of a signature runs eagerly (it picks cuDNN / cublasLt algorithms, which
+  // synchronises and cannot be captured).  DORPATCH_GRAPH=0 disables.
+  struct GraphEnt { int calls = 0; bool failed = false; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+  typedef std::tuple<int, int, int, int, const void*, const void*, const void*, const void*, float, float, int> GraphKey;
+  std::map<GraphKey, GraphEnt> graphs;
+  bool graphs_on = true;
+  int64_t graph_replays = 0;
+  std::string graph_msg;               // why the last capture attempt was abandoned (diagnostics)
+  void drop_graphs() {
+    for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    graphs.clear();
+  }
+
   std::map<std::pair<int, int>, CudnnPlan> cudnn_plans;                 // (layer id, N)
   std::map<std::tuple<int, int, int, int>, GemmPlan> gemm_plans;        // (rows, n_out, k, mode)
 
@@ -235,12 +254,14 @@ struct dp_engine {
   }
   void ensure_pin(size_t bytes) {
     if (bytes <= pin_bytes) return;
+    drop_graphs();                       // captured copies hold the old staging address
     if (pin) cudaFreeHost(pin);
     pin_bytes = std::max(bytes, (size_t)1 << 20);
     CUDA_OK(cudaMallocHost((void**)&pin, pin_bytes));
   }
   void ensure_samples(int n) {
     if (n <= cap_samples) return;
+    drop_graphs();                       // captured launches hold the old per-sample buffers
     // (old buffers stay in `allocs` and are released at destroy)
     cap_samples = std::max(n, cap_samples * 2);
     rects_d = (int16_t*)dmalloc((size_t)cap_samples * 16 * sizeof(int16_t));
@@ -343,7 +364,7 @@ struct dp_engine {
       L.x0 = dmalloc(n * Hp() * Hp() * STEM_CH * es);
       L.pool_amax = (int8_t*)dmalloc(n * Hp() * Hp() * STEM_CH);
       for (int i = 0; i < 4; ++i) L.g[i] = dmalloc(n * ma * es);
-      L.gn_partial = (float*)dmalloc(n * dp::GN_MAX_SPLITS * dp::GN_GROUPS * 2 * 4);
+      L.gn_partial = (float*)dmalloc((n * dp::GN_WS_FLOATS_PER_SAMPLE + dp::GN_WS_FLOATS_EXTRA) * 4);
       L.head_stats = (float*)dmalloc(n * dp::GN_GROUPS * 2 * 4);
       L.pooled = (float*)dmalloc(n * WIDTHS[3] * 4);
       L.dpooled = (float*)dmalloc(n * WIDTHS[3] * 4);
@@ -366,6 +387,9 @@ struct dp_engine {
     for (float** p : {&scale, &l2, &loss_struc, &loss_density, &group_lasso, &lr_d, &structured_d, &coeff_d, &helper_scale, &helper_l2})
       *p = (float*)dmalloc(B * 4);
     helper_ws = (float*)dmalloc(B * HW * 4);
+    failed_bits = (uint32_t*)dmalloc(B * FAILED_WORDS * 4);
+    CUDA_OK(cudaMemset(failed_bits, 0, B * FAILED_WORDS * 4));
+    failed_count = (int32_t*)dmalloc(B * 4); failed_nff = (int32_t*)dmalloc(B * 4); failed_active = (uint8_t*)dmalloc(B);
     win_dev = (float*)dmalloc(B * 64 * 4);
     grp_ss = (float*)dmalloc(B * (H / UNIT) * (H / UNIT) * 4);
     ensure_samples(chunk);
@@ -807,6 +831,7 @@ int32_t dp_engine_create(const dp_config* cfg, dp_engine** out) {
     e->fused_stem_bwd = e->own_stem && !(sb_env && strcmp(sb_env, "cudnn") == 0);
     const char* fg_env = getenv("DORPATCH_FUSED_GEMM");
     e->fused_gemm = e->bf16 && fg_env && atoi(fg_env) != 0;   // not validated on hardware yet: off unless asked for
+    if (const char* g_env = getenv("DORPATCH_GRAPH")) e->graphs_on = atoi(g_env) != 0;
     const char* pb_env = getenv("DORPATCH_POOL_BWD");
     // measured: rebuilding the d_stem patch in shared memory costs more than the saved HBM round trip
     // (2.25 ms vs 1.33 + 0.71 ms per 512-sample step) -> off unless DORPATCH_POOL_BWD=fused
@@ -847,6 +872,7 @@ void dp_engine_destroy(dp_engine* e) {
   };
   kill(e->stem);
   for (auto& b : e->blocks) { kill(b.ds); kill(b.c1); kill(b.c2); kill(b.c3); }
+  e->drop_graphs();
   for (auto& r : e->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto ev : e->prof_pool) cudaEventDestroy(ev);
   for (size_t l = 0; l < e->lanes.size(); ++l) {
@@ -873,6 +899,8 @@ int32_t dp_engine_load_weights(dp_engine* e, int32_t n, const char* const* names
 
 int64_t dp_engine_device_bytes(const dp_engine* e) { return e ? e->device_bytes : 0; }
 int64_t dp_engine_launch_count(const dp_engine* e) { return e ? e->launches : 0; }
+int64_t dp_engine_graph_replays(const dp_engine* e) { return e ? e->graph_replays : 0; }
+const char* dp_engine_graph_status(const dp_engine* e) { return e ? e->graph_msg.c_str() : ""; }
 
 int32_t dp_engine_profile(dp_engine* e, int32_t enable) {
   DP_TRY
@@ -1027,35 +1055,17 @@ int32_t dp_predict(dp_engine* e, const float* img, int32_t B, int32_t S, const i
   DP_CATCH
 }
 
-static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t st) {
-  if (!a) fail("null args");
-  e->check_B(a->B);
-  if (a->S < 1 || a->S_total < a->S) fail("bad S=%d / S_total=%d", a->S, a->S_total);
-  if (!a->x || !a->mask || !a->pattern || !a->grad_adv || !a->y_host || !a->targeted_host) fail("null pointer in dp_attack_args");
+// Everything dp_attack_grad puts on the stream: staging H2D copies, per-image kernels, the chunk loop on one or two
+// lanes, result D2H copies into the pinned staging area.  No host synchronisation inside (capturable).
+struct GradLayout { size_t rect_bytes, xf_bytes, d2h_off; int32_t* ys; uint8_t* tg; unsigned char* rp; };
+static void attack_grad_enqueue(dp_engine* e, const dp_attack_args* a, const GradLayout& L_, cudaStream_t st) {
   const int B = a->B, S = a->S, N = B * S, H = e->H;
-  e->ensure_samples(N);
-  // per-sample labels / criterion flags / rectangles -> device.  Pinned staging layout:
-  // [H2D region: ys | tg | rects][D2H region: results]; the regions never overlap.
-  const size_t rect_bytes = a->rects_host ? (size_t)N * 16 * sizeof(int16_t) : 0;
-  const size_t xf_bytes = a->xform_host ? (size_t)N * 8 * sizeof(float) : 0;
-  const size_t h2d_bytes = (((size_t)N * 5 + 15) / 16) * 16 + rect_bytes + xf_bytes;
-  const size_t d2h_off = (h2d_bytes + 255) / 256 * 256;
-  e->ensure_pin(d2h_off + (size_t)N * 8 + (size_t)B * 16 + 512);
-  int32_t* ys = (int32_t*)e->pin;
-  uint8_t* tg = (uint8_t*)(ys + N);
-  unsigned char* rp = (unsigned char*)e->pin + (((size_t)N * 5 + 15) / 16) * 16;
-  for (int b = 0; b < B; ++b)
-    if (a->y_host[b] < 0 || a->y_host[b] >= e->K) fail("label %lld of image %d outside [0,%d)", (long long)a->y_host[b], b, e->K);
-  for (int b = 0; b < B; ++b)
-    for (int s = 0; s < S; ++s) { ys[b * S + s] = (int32_t)a->y_host[b]; tg[b * S + s] = a->targeted_host[b]; }
-  if (rect_bytes) memcpy(rp, a->rects_host, rect_bytes);
-  CUDA_OK(cudaMemcpyAsync(e->y_d, ys, (size_t)N * 4, cudaMemcpyHostToDevice, st));
-  CUDA_OK(cudaMemcpyAsync(e->tg_d, tg, (size_t)N, cudaMemcpyHostToDevice, st));
-  if (rect_bytes) CUDA_OK(cudaMemcpyAsync(e->rects_d, rp, rect_bytes, cudaMemcpyHostToDevice, st));
+  const size_t rect_bytes = L_.rect_bytes, xf_bytes = L_.xf_bytes;
+  CUDA_OK(cudaMemcpyAsync(e->y_d, L_.ys, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->tg_d, L_.tg, (size_t)N, cudaMemcpyHostToDevice, st));
+  if (rect_bytes) CUDA_OK(cudaMemcpyAsync(e->rects_d, L_.rp, rect_bytes, cudaMemcpyHostToDevice, st));
   if (xf_bytes) {
-    unsigned char* xp = rp + rect_bytes;
-    memcpy(xp, a->xform_host, xf_bytes);
-    CUDA_OK(cudaMemcpyAsync(e->xf_d, xp, xf_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(e->xf_d, L_.rp + rect_bytes, xf_bytes, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemsetAsync(a->grad_adv, 0, (size_t)B * 3 * H * H * sizeof(float), st));   // the adjoint scatters with atomics
   }
   const int16_t* rects = rect_bytes ? e->rects_d : nullptr;
@@ -1113,23 +1123,90 @@ static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t
     e->use_lane(0);
     st = user_st;
   }
-  // results -> host (pinned staging, one sync)
-  unsigned char* out = e->pin + d2h_off;
+  // results -> host (pinned staging; the caller synchronises once)
+  unsigned char* out = e->pin + L_.d2h_off;
   size_t off = 0;
-  auto d2h = [&](const void* src, size_t bytes) { void* dst = out + off; CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st)); off += (bytes + 15) / 16 * 16; return dst; };
-  void* p_loss = d2h(e->loss_d, (size_t)N * 4);
-  void* p_pred = d2h(e->preds_d, (size_t)N * 4);
-  void* p_ls = d2h(e->loss_struc, (size_t)B * 4);
-  void* p_ld = d2h(e->loss_density, (size_t)B * 4);
-  void* p_gl = d2h(e->group_lasso, (size_t)B * 4);
-  void* p_l2 = d2h(e->l2, (size_t)B * 4);
+  auto d2h = [&](const void* src, size_t bytes) { CUDA_OK(cudaMemcpyAsync(out + off, src, bytes, cudaMemcpyDeviceToHost, st)); off += (bytes + 15) / 16 * 16; };
+  d2h(e->loss_d, (size_t)N * 4);
+  d2h(e->preds_d, (size_t)N * 4);
+  d2h(e->loss_struc, (size_t)B * 4);
+  d2h(e->loss_density, (size_t)B * 4);
+  d2h(e->group_lasso, (size_t)B * 4);
+  d2h(e->l2, (size_t)B * 4);
+}
+
+static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t st) {
+  if (!a) fail("null args");
+  e->check_B(a->B);
+  if (a->S < 1 || a->S_total < a->S) fail("bad S=%d / S_total=%d", a->S, a->S_total);
+  if (!a->x || !a->mask || !a->pattern || !a->grad_adv || !a->y_host || !a->targeted_host) fail("null pointer in dp_attack_args");
+  const int B = a->B, S = a->S, N = B * S;
+  e->ensure_samples(N);
+  // per-sample labels / criterion flags / rectangles -> pinned staging.  Layout:
+  // [H2D region: ys | tg | rects | xforms][D2H region: results]; the regions never overlap.
+  GradLayout L_;
+  L_.rect_bytes = a->rects_host ? (size_t)N * 16 * sizeof(int16_t) : 0;
+  L_.xf_bytes = a->xform_host ? (size_t)N * 8 * sizeof(float) : 0;
+  const size_t h2d_bytes = (((size_t)N * 5 + 15) / 16) * 16 + L_.rect_bytes + L_.xf_bytes;
+  L_.d2h_off = (h2d_bytes + 255) / 256 * 256;
+  e->ensure_pin(L_.d2h_off + (size_t)N * 8 + (size_t)B * 16 + 512);
+  L_.ys = (int32_t*)e->pin;
+  L_.tg = (uint8_t*)(L_.ys + N);
+  L_.rp = (unsigned char*)e->pin + (((size_t)N * 5 + 15) / 16) * 16;
+  for (int b = 0; b < B; ++b)
+    if (a->y_host[b] < 0 || a->y_host[b] >= e->K) fail("label %lld of image %d outside [0,%d)", (long long)a->y_host[b], b, e->K);
+  for (int b = 0; b < B; ++b)
+    for (int s = 0; s < S; ++s) { L_.ys[b * S + s] = (int32_t)a->y_host[b]; L_.tg[b * S + s] = a->targeted_host[b]; }
+  if (L_.rect_bytes) memcpy(L_.rp, a->rects_host, L_.rect_bytes);
+  if (L_.xf_bytes) memcpy(L_.rp + L_.rect_bytes, a->xform_host, L_.xf_bytes);
+
+  bool done = false;
+  if (e->graphs_on && !e->prof_on && !L_.xf_bytes) {
+    dp_engine::GraphKey key{B, S, a->S_total, a->stage, a->x, a->mask, a->pattern, a->grad_adv, a->eps, a->confidence, L_.rect_bytes ? 1 : 0};
+    dp_engine::GraphEnt& ent = e->graphs[key];
+    ++ent.calls;
+    if (ent.exec != nullptr) {
+      CUDA_OK(cudaGraphLaunch(ent.exec, st));
+      e->launches += ent.launches; ++e->graph_replays;
+      done = true;
+    } else if (!ent.failed && ent.calls >= 2) {          // call 1 ran eagerly: every plan / algorithm choice exists now
+      const int64_t l0 = e->launches;
+      cudaGraph_t graph = nullptr;
+      bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        try { attack_grad_enqueue(e, a, L_, st); } catch (const std::exception& ex) { ok = false; e->graph_msg = std::string("enqueue: ") + ex.what(); }
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (ce != cudaSuccess || graph == nullptr) { if (ok) e->graph_msg = std::string("end capture: ") + cudaGetErrorString(ce); ok = false; }
+      } else e->graph_msg = "begin capture failed";
+      if (ok) {
+        const cudaError_t ci = cudaGraphInstantiate(&ent.exec, graph, 0);
+        if (ci != cudaSuccess) { ok = false; ent.exec = nullptr; e->graph_msg = std::string("instantiate: ") + cudaGetErrorString(ci); }
+      }
+      if (graph) cudaGraphDestroy(graph);
+      if (ok) {
+        ent.launches = e->launches - l0;
+        CUDA_OK(cudaGraphLaunch(ent.exec, st));
+        ++e->graph_replays;
+        done = true;
+      } else {
+        cudaGetLastError();                                // clear the capture error; fall back to eager launches for this signature
+        e->launches = l0;
+        e->use_lane(0);
+        ent.failed = true;
+      }
+    }
+  }
+  if (!done) attack_grad_enqueue(e, a, L_, st);
   CUDA_OK(cudaStreamSynchronize(st));
-  if (a->loss_adv_host) memcpy(a->loss_adv_host, p_loss, (size_t)N * 4);
-  if (a->preds_host) memcpy(a->preds_host, p_pred, (size_t)N * 4);
-  if (a->loss_struc_host) memcpy(a->loss_struc_host, p_ls, (size_t)B * 4);
-  if (a->stage == 0 && a->loss_density_host) memcpy(a->loss_density_host, p_ld, (size_t)B * 4);
-  if (a->stage == 0 && a->group_lasso_host) memcpy(a->group_lasso_host, p_gl, (size_t)B * 4);
-  if (a->l2_host) memcpy(a->l2_host, p_l2, (size_t)B * 4);
+  unsigned char* out = e->pin + L_.d2h_off;
+  size_t off = 0;
+  auto take = [&](void* dst, size_t bytes, bool want) { if (want && dst) memcpy(dst, out + off, bytes); off += (bytes + 15) / 16 * 16; };
+  take(a->loss_adv_host, (size_t)N * 4, true);
+  take(a->preds_host, (size_t)N * 4, true);
+  take(a->loss_struc_host, (size_t)B * 4, true);
+  take(a->loss_density_host, (size_t)B * 4, a->stage == 0);
+  take(a->group_lasso_host, (size_t)B * 4, a->stage == 0);
+  take(a->l2_host, (size_t)B * 4, true);
 }
 
 static void attack_update_impl(dp_engine* e, const dp_update_args* u, cudaStream_t st) {
@@ -1206,6 +1283,72 @@ int32_t dp_net_forward_backward(dp_engine* e, const float* z, int32_t N, float* 
     e->backward(N, dlogits_dev, st);
     dp::launch_unpack_nhwc(e->d_input, dz_dev, N, e->H, e->H, e->Cpd, e->bf16, st); KERNEL_OK(); ++e->launches;
   }
+  DP_CATCH
+}
+
+/* ---- failed-mask sets on the device (attack.py:96,187-190,259-267) ------------------------------------- */
+int32_t dp_failed_set_write(dp_engine* e, int32_t b, const int32_t* idx_host, int32_t n, void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  if (b < 0 || b >= e->cfg.max_images) fail("image %d outside [0, max_images=%d)", b, e->cfg.max_images);
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<uint32_t> w(dp_engine::FAILED_WORDS, 0u);
+  for (int i = 0; i < n; ++i) {
+    if (idx_host[i] < 0 || idx_host[i] >= dp_engine::FAILED_WORDS * 32) fail("mask index %d outside [0, %d)", idx_host[i], dp_engine::FAILED_WORDS * 32);
+    w[idx_host[i] >> 5] |= 1u << (idx_host[i] & 31);
+  }
+  CUDA_OK(cudaMemcpyAsync(e->failed_bits + (size_t)b * dp_engine::FAILED_WORDS, w.data(), w.size() * 4, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  DP_CATCH
+}
+
+int32_t dp_failed_set_update(dp_engine* e, int32_t B, int32_t S, const int32_t* idx_host, const int32_t* nff_host, const uint8_t* active_host,
+                             const float* loss_host, float thresh, int32_t* count_host, void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  e->check_B(B);
+  if (S < 1 || !idx_host || !nff_host || !active_host || !count_host) fail("dp_failed_set_update: bad arguments");
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = B * S;
+  if (N > e->failed_cap) {
+    e->failed_cap = std::max(N, e->failed_cap * 2);
+    e->failed_idx = (int32_t*)e->dmalloc((size_t)e->failed_cap * 4);
+    e->failed_loss = (float*)e->dmalloc((size_t)e->failed_cap * 4);
+  }
+  for (int i = 0; i < N; ++i)
+    if (idx_host[i] < 0 || idx_host[i] >= dp_engine::FAILED_WORDS * 32) fail("mask index %d outside [0, %d)", idx_host[i], dp_engine::FAILED_WORDS * 32);
+  CUDA_OK(cudaMemcpyAsync(e->failed_idx, idx_host, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->failed_nff, nff_host, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(e->failed_active, active_host, (size_t)B, cudaMemcpyHostToDevice, st));
+  const float* loss = e->loss_d;                       // default: the per-sample CW losses the last dp_attack_grad left on the device
+  if (loss_host != nullptr) {                          // EOT-sharded runs pass the all-gathered losses
+    CUDA_OK(cudaMemcpyAsync(e->failed_loss, loss_host, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    loss = e->failed_loss;
+  } else if (N > e->cap_samples) fail("dp_failed_set_update: no device losses for %d samples", N);
+  dp::launch_failed_update(e->failed_bits, dp_engine::FAILED_WORDS, e->failed_idx, loss, e->failed_nff, e->failed_active, B, S, thresh,
+                           e->failed_count, st);
+  KERNEL_OK(); ++e->launches;
+  CUDA_OK(cudaMemcpyAsync(count_host, e->failed_count, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  DP_CATCH
+}
+
+int32_t dp_failed_set_read(dp_engine* e, int32_t b, int32_t* idx_host_out, int32_t cap, int32_t* n_out, void* stream) {
+  DP_TRY
+  if (!e) fail("null engine");
+  if (b < 0 || b >= e->cfg.max_images) fail("image %d outside [0, max_images=%d)", b, e->cfg.max_images);
+  CUDA_OK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<uint32_t> w(dp_engine::FAILED_WORDS);
+  CUDA_OK(cudaMemcpyAsync(w.data(), e->failed_bits + (size_t)b * dp_engine::FAILED_WORDS, w.size() * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  int n = 0;
+  for (int i = 0; i < dp_engine::FAILED_WORDS * 32; ++i)
+    if (w[i >> 5] & (1u << (i & 31))) { if (n < cap && idx_host_out) idx_host_out[n] = i; ++n; }
+  if (n_out) *n_out = n;
+  if (n > cap && idx_host_out) fail("dp_failed_set_read: %d indices, buffer holds %d", n, cap);
   DP_CATCH
 }
 

@@ -8,6 +8,10 @@ namespace dp {
 
 constexpr int GN_GROUPS = 32;
 constexpr int GN_MAX_SPLITS = 16;
+// GroupNorm scratch (`partial`): N * GN_WS_FLOATS_PER_SAMPLE + GN_WS_FLOATS_EXTRA floats (v3: per-tile partial sums,
+// per-sample backward means, the work / done / ready counters; also covers the two-pass kernels' split partials)
+constexpr int GN_WS_FLOATS_PER_SAMPLE = 8192;
+constexpr int GN_WS_FLOATS_EXTRA = 4096;
 
 // ---- classifier-side kernels (kernels_net.cu) --------------------------------------
 // timm StdConv2d standardisation of OIHW fp32 weights -> KRSC (NHWC filter), channel-padded.
@@ -28,6 +32,8 @@ void launch_gn_stats(const void* x, float* partial, float* stats, int N, int P, 
 void launch_gn_relu_backward(const void* dy, const void* x, const void* addend, void* dx, const float* gamma,
                              const float* beta, const float* stats, float* partial, int N, int P, int C, bool bf16,
                              cudaStream_t st, bool gamma_pos = false);
+// profiling aid (tools/gnbench.cu): device buffer [CTAs][8] that receives clock64 stamps at the v2 forward kernel's phase boundaries
+void gn2_set_trace(unsigned long long* dev_ptr);
 // ConstantPad2d(1,0)+MaxPool(3,2): x [N,Hs,Ws,C] -> y [N,Hs/2,Ws/2,C]; argmax (int8, 0..8) optional.
 void launch_maxpool_forward(const void* x, void* y, int8_t* amax, int N, int Hs, int Ws, int C, bool bf16,
                             cudaStream_t st);
@@ -94,6 +100,9 @@ void launch_update(const float* x, float* mask, float* pattern, const float* G, 
                    const float* scale, const float* win_dev, const float* grp_ss, const float* lr,
                    const float* structured, const float* coeff_gl, float density, float lo, float hi, int stage,
                    float* gp_out, float* gm_out, const float* gp_bias, int B, int H, int W, int unit, cudaStream_t st);
+// failed-mask bitmap update of one step (attack.py:259-267) + popcount per image
+void launch_failed_update(uint32_t* bits, int words, const int32_t* idx, const float* loss, const int32_t* nff, const uint8_t* active,
+                          int B, int S, float thresh, int32_t* count, cudaStream_t st);
 // k x k window sums of [B,1,H,W] (optionally of the squares)
 void launch_window_sum(const float* t, float* out, int B, int H, int W, int k, bool square, cudaStream_t st);
 

@@ -1172,6 +1172,8 @@ void launch_subsample2_adjoint_add(const void* dy, void* dx, int N, int H, int W
 // Statistics and every sum stay fp32.
 // ====================================================================================
 namespace gn2 {
+__device__ unsigned long long* g_trace = nullptr;   // optional phase trace (tools/gnbench.cu): [CTA][8] clock64 stamps
+#define GN2_STAMP(i) do { if (g_trace != nullptr && threadIdx.x == 0) g_trace[(size_t)blockIdx.x * 8 + (i)] = clock64(); } while (0)
 constexpr uint32_t CHUNK = 32768;
 constexpr int MAX_CHUNKS = 7;                      // <= 224 KB per slab
 constexpr int OFF_BAR_X = 0, OFF_BAR_D = 64, OFF_PART = 128, OFF_SA = 384, OFF_SB = 512, OFF_FLAG = 640;
@@ -1265,11 +1267,66 @@ template <> struct Acc<__nv_bfloat16> {
   }
 };
 
-// Deterministic CTA reduction of per-thread per-channel accumulators to per-group sums (as gnc::cta_group_reduce,
-// for a linear thread -> column mapping: column = threadIdx.x % cols).
+// Deterministic CTA reduction of per-thread per-channel accumulators (a[V], b[V]) to the 32 per-group sums, for the
+// linear thread -> column mapping (column = threadIdx.x % cols): fixed xor-shuffle tree inside each warp, one
+// shared-memory exchange, fixed-order sum over the warps.  ~300 cycles; the shared-memory loop of gnc::cta_group_reduce
+// it replaces took 3-9k cycles per slab (phase trace, profiles/r02_gn_v2_trace.txt).  red: >= (blockDim/32) * 64 floats.
 template <int V>
-__device__ __forceinline__ void group_reduce(const float* a, const float* b, int C, float* tp, float* part) {
-  gnc::cta_group_reduce<V>(a, b, C, tp, part);   // identical indexing: thread t = row * cols + column
+__device__ __forceinline__ void group_reduce(const float* a, const float* b, int C, float* red, float* part) {
+  const int cols = C / V, cpg = C / GN_GROUPS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)blockDim.x >> 5;
+  if (cpg <= V) {
+    // each thread holds gpt = V / cpg whole groups; threads of one column sit `cols` lanes apart (cols <= 32)
+    const int gpt = V / cpg;
+    float sa[gnc::MAX_GPT], sb[gnc::MAX_GPT];
+#pragma unroll
+    for (int j = 0; j < gnc::MAX_GPT; ++j) {
+      sa[j] = 0.f; sb[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i)
+        if (i / cpg == j) { sa[j] += a[i]; sb[j] += b[i]; }
+    }
+    for (int o = cols; o < 32; o <<= 1) {
+#pragma unroll
+      for (int j = 0; j < gnc::MAX_GPT; ++j) {
+        sa[j] += __shfl_xor_sync(0xffffffffu, sa[j], o);
+        sb[j] += __shfl_xor_sync(0xffffffffu, sb[j], o);
+      }
+    }
+    __syncthreads();                                  // `red` may still be read by the previous use
+    if (lane < cols) {
+#pragma unroll
+      for (int j = 0; j < gnc::MAX_GPT; ++j)
+        if (j < gpt) { red[warp * 64 + (lane * gpt + j) * 2 + 0] = sa[j]; red[warp * 64 + (lane * gpt + j) * 2 + 1] = sb[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float t = 0.f;
+      for (int w = 0; w < nw; ++w) t += red[w * 64 + threadIdx.x];
+      part[threadIdx.x] = t;
+    }
+  } else {
+    // a group spans L = cpg / V consecutive columns = consecutive lanes; a pixel row spans cols / 32 = L warps
+    const int L = cpg / V;
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) { sa += a[i]; sb += b[i]; }
+    for (int o = 1; o < L; o <<= 1) {
+      sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    __syncthreads();
+    const int gpw = 32 / L;                           // groups per warp
+    if ((lane & (L - 1)) == 0) { red[warp * 64 + (lane / L) * 2 + 0] = sa; red[warp * 64 + (lane / L) * 2 + 1] = sb; }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int g = threadIdx.x >> 1, comp = threadIdx.x & 1;
+      const int cb = (g * L) >> 5, slot = g % gpw;    // column block (warp index mod L) and slot inside the warp's row
+      float t = 0.f;
+      for (int w = cb; w < nw; w += L) t += red[w * 64 + slot * 2 + comp];
+      part[threadIdx.x] = t;
+    }
+  }
 }
 
 // ---- forward --------------------------------------------------------------------------------------
@@ -1295,7 +1352,9 @@ __global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) fwd_kernel(const T* __r
   const int p0 = (int)(((long long)P * rank) / CL), p1 = (int)(((long long)P * (rank + 1)) / CL);
   const uint32_t slab_bytes = (uint32_t)((size_t)(p1 - p0) * C * sizeof(T));
   const size_t gbase = ((size_t)n * P + p0) * C * sizeof(T);          // byte offset of the slab in x / y
+  GN2_STAMP(0);
   if (threadIdx.x == 0) {
+    *reinterpret_cast<unsigned long long*>(smem + OFF_FLAG) = 0ull;
     for (int k = 0; k < MAX_CHUNKS; ++k) bar_init(sb0 + OFF_BAR_X + 8 * k);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1333,15 +1392,22 @@ __global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) fwd_kernel(const T* __r
 #pragma unroll
     for (int i = 0; i < V; ++i) { a[i] += f[i]; bq[i] = fmaf(f[i], f[i], bq[i]); }
   }
+  GN2_STAMP(1);
+  if (g_trace != nullptr && (threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(smem + OFF_FLAG), (unsigned long long)clock64());
   group_reduce<V>(a, bq, C, tp, part);
+  if (g_trace != nullptr && threadIdx.x == 0) g_trace[(size_t)blockIdx.x * 8 + 2] = *reinterpret_cast<unsigned long long*>(smem + OFF_FLAG);   // slowest warp's loop end
+  GN2_STAMP(3);
   cluster.sync();
+  GN2_STAMP(4);
   if (threadIdx.x < GN_GROUPS) {
+    float2 rv[16];                                                    // all ranks' partials in flight at once (DSMEM ~215 cycles each)
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      if (r < CL) rv[r] = *reinterpret_cast<const float2*>(cluster.map_shared_rank(part, r) + threadIdx.x * 2);
     float s = 0.f, q = 0.f;
-    for (int r = 0; r < CL; ++r) {
-      const float* rp = cluster.map_shared_rank(part, r);
-      s += rp[threadIdx.x * 2 + 0];
-      q += rp[threadIdx.x * 2 + 1];
-    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      if (r < CL) { s += rv[r].x; q += rv[r].y; }
     const float cnt = (float)P * cpg;
     const float mean = s / cnt;
     float var = q / cnt - mean * mean;
@@ -1363,6 +1429,7 @@ __global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) fwd_kernel(const T* __r
     sa[i] = s_rstd[g] * gamma[c];
     sb[i] = beta[c] - s_mean[g] * sa[i];
   }
+  GN2_STAMP(5);
   sp = slab + threadIdx.x * 16;
   char* dst = reinterpret_cast<char*>(y) + gbase + (size_t)threadIdx.x * 16;
   const uint32_t full_groups = iters / IPC;
@@ -1376,7 +1443,9 @@ __global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) fwd_kernel(const T* __r
   }
   for (uint32_t j = full_groups * IPC; j < iters + (threadIdx.x < rem ? 1u : 0u); ++j, sp += TH * 16, dst += TH * 16)
     *reinterpret_cast<uint4*>(dst) = A::apply_relu(lds128(sp), sa, sb);
+  GN2_STAMP(6);
   cluster.barrier_wait();                                             // every peer has read our partials: we may exit
+  GN2_STAMP(7);
 }
 
 // ---- backward -------------------------------------------------------------------------------------
@@ -1511,12 +1580,14 @@ __global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) bwd_kernel(const T* __r
   group_reduce<V>(a, bq, C, tp, part);
   cluster.sync();
   if (threadIdx.x < GN_GROUPS) {
+    float2 rv[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      if (r < CL) rv[r] = *reinterpret_cast<const float2*>(cluster.map_shared_rank(part, r) + threadIdx.x * 2);
     float s = 0.f, q = 0.f;
-    for (int r = 0; r < CL; ++r) {
-      const float* rp = cluster.map_shared_rank(part, r);
-      s += rp[threadIdx.x * 2 + 0];
-      q += rp[threadIdx.x * 2 + 1];
-    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+      if (r < CL) { s += rv[r].x; q += rv[r].y; }
     const float inv_m = 1.0f / ((float)P * cpg);
     s_1[threadIdx.x] = s * inv_m;
     s_2[threadIdx.x] = q * inv_m;
@@ -1579,11 +1650,298 @@ __global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) bwd_kernel(const T* __r
 struct Plan { int cl, threads; bool dys; size_t smem; uint32_t stride; };
 }  // namespace gn2
 
-static int g_gn_version = -1;   // DORPATCH_GN: v2 (default), v1 (round-1 cluster kernels), twopass
+
+// ====================================================================================
+// GroupNorm v3: streaming two-phase kernel, second read from L2 (no clusters, no slab in shared memory).
+// Phase traces of v2 (tools/gnbench.cu, profiles/r02_gn_v2_trace.txt) show where a cluster-per-sample kernel loses:
+// one 200 KB slab per SM serialises load -> statistics -> cluster barrier (2-3k cycles of skew) -> DSMEM finalize ->
+// apply, clusters of 8 strand 20 of 148 SMs (GPCs hold 16-20 SMs), and 16 warps per SM cannot hide any of it --
+// while a plain two-pass pair of kernels streams at 90 % of peak but moves 3 units instead of 2.  v3 keeps the
+// streaming structure AND the 2-unit traffic: a persistent grid pulls work items (sample, 32-64 KB tile, phase) from a
+// global counter, ordered so that a group of G samples (G x sample bytes ~ 24 MB, far inside the 126 MB L2) has all its
+// phase-1 items (read x, per-tile group sums -> global partials, count) ahead of its phase-2 items (wait for the
+// sample's statistics flag, re-read the tile -- an L2 hit --, normalise, write).  The last tile of a sample reduces the
+// partials in tile order (deterministic) and publishes mean / rstd.  Phase-1 items never wait, items are handed out in
+// order, so a phase-2 item only ever waits for items already running: no co-residency assumption, no deadlock.
+// HBM traffic: forward 1 read + 1 write, backward reads of x, dy (+ addend) + 1 write.
+// ====================================================================================
+namespace gn3 {
+using gn2::Acc;
+constexpr int TH = 256;
+constexpr int CTL_WORDS = 32;   // [0] work counter; done[n] at CTL_WORDS + n; ready[n] at CTL_WORDS + N + n
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+struct Item { int n, t, phase; };
+__device__ __forceinline__ bool next_item(unsigned* ctl, unsigned* s_item, int N, int G, int tiles, Item& it) {
+  __syncthreads();                                   // everyone is done with the previous item (and with *s_item)
+  if (threadIdx.x == 0) *s_item = atomicAdd(ctl, 1u);
+  __syncthreads();
+  const unsigned i = *s_item, per = 2u * (unsigned)G * (unsigned)tiles;
+  const unsigned g = i / per;
+  const int n0 = (int)g * G;
+  if (n0 >= N) return false;
+  const int ng = min(G, N - n0);
+  unsigned r = i - g * per;
+  if (r >= 2u * (unsigned)ng * (unsigned)tiles) return false;      // past the (partial) last group
+  it.phase = r >= (unsigned)ng * (unsigned)tiles ? 1 : 0;
+  r -= (unsigned)it.phase * (unsigned)ng * (unsigned)tiles;
+  it.n = n0 + (int)(r / (unsigned)tiles);
+  it.t = (int)(r % (unsigned)tiles);
+  return true;
+}
+// per-tile group sums -> global partial; the sample's last tile reduces all partials in tile order and publishes
+// out2[n][g] = finish(sum_a, sum_b); then raises ready[n].
+template <int V, typename F>
+__device__ __forceinline__ void publish(const float* a, const float* b, int C, float* tp, float* part, float* partial,
+                                        unsigned* ctl, int N, int n, int t, int tiles, unsigned* s_flag, float* out2, F&& finish) {
+  gnc::cta_group_reduce<V>(a, b, C, tp, part);
+  float* pt = partial + ((size_t)n * tiles + t) * (GN_GROUPS * 2);
+  if (threadIdx.x < GN_GROUPS) {
+    pt[threadIdx.x * 2 + 0] = part[threadIdx.x * 2 + 0];
+    pt[threadIdx.x * 2 + 1] = part[threadIdx.x * 2 + 1];
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *s_flag = (atomicAdd(ctl + CTL_WORDS + n, 1u) == (unsigned)(tiles - 1)) ? 1u : 0u;
+  __syncthreads();
+  if (*s_flag) {
+    if (threadIdx.x < GN_GROUPS) {
+      __threadfence();
+      float sa = 0.f, sb = 0.f;
+      const float* pn = partial + (size_t)n * tiles * (GN_GROUPS * 2);
+      for (int k = 0; k < tiles; ++k) {
+        sa += __ldcg(pn + (size_t)k * (GN_GROUPS * 2) + threadIdx.x * 2 + 0);
+        sb += __ldcg(pn + (size_t)k * (GN_GROUPS * 2) + threadIdx.x * 2 + 1);
+      }
+      float o0, o1;
+      finish(sa, sb, o0, o1);
+      out2[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 0] = o0;
+      out2[((size_t)n * GN_GROUPS + threadIdx.x) * 2 + 1] = o1;
+      __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) atomicExch(ctl + CTL_WORDS + N + n, 1u);
+  }
+}
+__device__ __forceinline__ void wait_ready(unsigned* ctl, int N, int n) {
+  if (threadIdx.x == 0) while (ld_acquire(ctl + CTL_WORDS + N + n) == 0u) __nanosleep(100);
+  __syncthreads();
+}
+
+template <typename T, int ITER>
+__global__ void __launch_bounds__(TH, 4) fwd_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ gamma,
+                                                 const float* __restrict__ beta, float* __restrict__ stats, float* __restrict__ partial,
+                                                 unsigned* __restrict__ ctl, int N, int P, int C, int G, int tiles) {
+  using A = Acc<T>;
+  constexpr int V = A::V;
+  constexpr int UB = 8;                                  // vectors in flight per thread
+  __shared__ float tp[TH * gnc::MAX_GPT * 2];
+  __shared__ float part[GN_GROUPS * 2];
+  __shared__ unsigned s_item, s_flag;
+  const int cols = C / V, cpg = C / GN_GROUPS, tcol = threadIdx.x % cols;
+  const uint32_t sample_vecs = (uint32_t)P * cols;
+  const float cnt = (float)P * cpg;
+  Item it;
+  while (next_item(ctl, &s_item, N, G, tiles, it)) {
+    const char* xs = reinterpret_cast<const char*>(x) + (size_t)it.n * sample_vecs * 16;
+    const uint32_t v0 = (uint32_t)it.t * TH * ITER + threadIdx.x;
+    if (it.phase == 0) {
+      float a[V], bq[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) { a[i] = 0.f; bq[i] = 0.f; }
+#pragma unroll
+      for (int j0 = 0; j0 < ITER; j0 += UB) {
+        uint4 v[UB];
+#pragma unroll
+        for (int j = 0; j < UB; ++j) {
+          const uint32_t vi = v0 + (j0 + j) * TH;
+          v[j] = vi < sample_vecs ? gn2::ldg128(xs + (size_t)vi * 16) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < UB; ++j) {
+          float f[V]; A::unpack(v[j], f);
+#pragma unroll
+          for (int i = 0; i < V; ++i) { a[i] += f[i]; bq[i] = fmaf(f[i], f[i], bq[i]); }
+        }
+      }
+      publish<V>(a, bq, C, tp, part, partial, ctl, N, it.n, it.t, tiles, &s_flag, stats, [&](float s, float q, float& o0, float& o1) {
+        const float mean = s / cnt;
+        float var = q / cnt - mean * mean;
+        var = var < 0.f ? 0.f : var;
+        o0 = mean; o1 = rsqrtf(var + 1e-5f);
+      });
+    } else {
+      wait_ready(ctl, N, it.n);
+      float sa[V], sb[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = tcol * V + i, g = c / cpg;
+        const float mean = __ldcg(stats + ((size_t)it.n * GN_GROUPS + g) * 2), rstd = __ldcg(stats + ((size_t)it.n * GN_GROUPS + g) * 2 + 1);
+        sa[i] = rstd * gamma[c];
+        sb[i] = beta[c] - mean * sa[i];
+      }
+      char* ys = reinterpret_cast<char*>(y) + (size_t)it.n * sample_vecs * 16;
+#pragma unroll
+      for (int j0 = 0; j0 < ITER; j0 += UB) {
+        uint4 v[UB];
+#pragma unroll
+        for (int j = 0; j < UB; ++j) {
+          const uint32_t vi = v0 + (j0 + j) * TH;
+          v[j] = vi < sample_vecs ? gn2::ldg128(xs + (size_t)vi * 16) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < UB; ++j) {
+          const uint32_t vi = v0 + (j0 + j) * TH;
+          if (vi < sample_vecs) *reinterpret_cast<uint4*>(ys + (size_t)vi * 16) = A::apply_relu(v[j], sa, sb);
+        }
+      }
+    }
+  }
+}
+
+// backward: phase 1 sums dg and dg*xhat per group (dg = dy * gate * gamma), phase 2 writes dx = k1*dym + k2*x + k3 (+ addend)
+template <typename T, int ITER, bool NEG>
+__global__ void __launch_bounds__(TH, 3) bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ addend,
+                                                 T* __restrict__ dx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                 const float* __restrict__ stats, float* __restrict__ partial, float* __restrict__ m12,
+                                                 unsigned* __restrict__ ctl, int N, int P, int C, int G, int tiles) {
+  using A = Acc<T>;
+  constexpr int V = A::V;
+  constexpr bool PACKED = sizeof(T) == 2 && !NEG;
+  constexpr int UB = 4;
+  __shared__ float tp[TH * gnc::MAX_GPT * 2];
+  __shared__ float part[GN_GROUPS * 2];
+  __shared__ unsigned s_item, s_flag;
+  const int cols = C / V, cpg = C / GN_GROUPS, tcol = threadIdx.x % cols;
+  const uint32_t sample_vecs = (uint32_t)P * cols;
+  const float inv_m = 1.0f / ((float)P * cpg);
+  Item it;
+  while (next_item(ctl, &s_item, N, G, tiles, it)) {
+    const size_t sbase = (size_t)it.n * sample_vecs * 16;
+    const char* xs = reinterpret_cast<const char*>(x) + sbase;
+    const char* ds = reinterpret_cast<const char*>(dy) + sbase;
+    const uint32_t v0 = (uint32_t)it.t * TH * ITER + threadIdx.x;
+    // ReLU-gate constants of this sample's channels
+    float sa[PACKED ? 1 : V], sbv[PACKED ? 1 : V];
+    uint32_t thr[V / 2 > 0 ? V / 2 : 1];
+    {
+      float sa_[V], sb_[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = tcol * V + i, g = c / cpg;
+        const float mean = stats[((size_t)it.n * GN_GROUPS + g) * 2 + 0], rstd = stats[((size_t)it.n * GN_GROUPS + g) * 2 + 1];
+        sa_[i] = rstd * gamma[c];
+        sb_[i] = beta[c] - mean * sa_[i];
+      }
+      if (PACKED) {
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i)
+          thr[i] = gn2::floor_bf16_bits(-sb_[2 * i] / sa_[2 * i]) | (gn2::floor_bf16_bits(-sb_[2 * i + 1] / sa_[2 * i + 1]) << 16);
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) { sa[PACKED ? 0 : i] = sa_[i]; sbv[PACKED ? 0 : i] = sb_[i]; }
+      }
+    }
+    auto gate = [&](const uint4& vx, const uint4& vd, float* fx, float* fd) {
+      A::unpack(vx, fx);
+      if (PACKED) {
+        uint4 m;
+        m.x = vd.x & gn2::gt2_mask(vx.x, thr[0]); m.y = vd.y & gn2::gt2_mask(vx.y, thr[1]);
+        m.z = vd.z & gn2::gt2_mask(vx.z, thr[V / 2 > 2 ? 2 : 0]); m.w = vd.w & gn2::gt2_mask(vx.w, thr[V / 2 > 3 ? 3 : 0]);
+        A::unpack(m, fd);
+      } else {
+        A::unpack(vd, fd);
+#pragma unroll
+        for (int i = 0; i < V; ++i) fd[i] = fmaf(sa[PACKED ? 0 : i], fx[i], sbv[PACKED ? 0 : i]) > 0.f ? fd[i] : 0.f;
+      }
+    };
+    if (it.phase == 0) {
+      float a[V], bq[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) { a[i] = 0.f; bq[i] = 0.f; }
+#pragma unroll
+      for (int j0 = 0; j0 < ITER; j0 += UB) {
+        uint4 vx[UB], vd[UB];
+#pragma unroll
+        for (int j = 0; j < UB; ++j) {
+          const uint32_t vi = v0 + (j0 + j) * TH;
+          const bool in = vi < sample_vecs;
+          vx[j] = in ? gn2::ldg128(xs + (size_t)vi * 16) : make_uint4(0u, 0u, 0u, 0u);
+          vd[j] = in ? gn2::ldg128(ds + (size_t)vi * 16) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < UB; ++j) {
+          float fx[V], fd[V]; gate(vx[j], vd[j], fx, fd);
+#pragma unroll
+          for (int i = 0; i < V; ++i) { a[i] += fd[i]; bq[i] = fmaf(fd[i], fx[i], bq[i]); }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = tcol * V + i, g = c / cpg;
+        const float mean = stats[((size_t)it.n * GN_GROUPS + g) * 2 + 0], rstd = stats[((size_t)it.n * GN_GROUPS + g) * 2 + 1];
+        const float ga = gamma[c], A_ = a[i];
+        a[i] = ga * A_;
+        bq[i] = rstd * ga * (bq[i] - mean * A_);
+      }
+      publish<V>(a, bq, C, tp, part, partial, ctl, N, it.n, it.t, tiles, &s_flag, m12,
+                 [&](float s, float q, float& o0, float& o1) { o0 = s * inv_m; o1 = q * inv_m; });
+    } else {
+      wait_ready(ctl, N, it.n);
+      float k1[V], k2[V], k3[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = tcol * V + i, g = c / cpg;
+        const float mean = stats[((size_t)it.n * GN_GROUPS + g) * 2 + 0], rstd = stats[((size_t)it.n * GN_GROUPS + g) * 2 + 1];
+        const float m1 = __ldcg(m12 + ((size_t)it.n * GN_GROUPS + g) * 2), m2 = __ldcg(m12 + ((size_t)it.n * GN_GROUPS + g) * 2 + 1);
+        k1[i] = rstd * gamma[c];
+        k2[i] = -rstd * rstd * m2;
+        k3[i] = -rstd * m1 - k2[i] * mean;
+      }
+      char* os = reinterpret_cast<char*>(dx) + sbase;
+      const char* as = addend ? reinterpret_cast<const char*>(addend) + sbase : nullptr;
+      const bool has_add = as != nullptr;
+#pragma unroll
+      for (int j0 = 0; j0 < ITER; j0 += UB) {
+        uint4 vx[UB], vd[UB], va[UB];
+#pragma unroll
+        for (int j = 0; j < UB; ++j) {
+          const uint32_t vi = v0 + (j0 + j) * TH;
+          const bool in = vi < sample_vecs;
+          vx[j] = in ? gn2::ldg128(xs + (size_t)vi * 16) : make_uint4(0u, 0u, 0u, 0u);
+          vd[j] = in ? gn2::ldg128(ds + (size_t)vi * 16) : make_uint4(0u, 0u, 0u, 0u);
+          if (has_add) va[j] = in ? gn2::ldg128(as + (size_t)vi * 16) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < UB; ++j) {
+          const uint32_t vi = v0 + (j0 + j) * TH;
+          float fx[V], fd[V], fo[V];
+          gate(vx[j], vd[j], fx, fd);
+          if (has_add) A::unpack(va[j], fo);
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const float tt = fmaf(k1[i], fd[i], fmaf(k2[i], fx[i], k3[i]));
+            fo[i] = has_add ? fo[i] + tt : tt;
+          }
+          if (vi < sample_vecs) *reinterpret_cast<uint4*>(os + (size_t)vi * 16) = A::pack(fo);
+        }
+      }
+    }
+  }
+}
+}  // namespace gn3
+
+void gn2_set_trace(unsigned long long* dev_ptr) { cudaMemcpyToSymbol(gn2::g_trace, &dev_ptr, sizeof(dev_ptr)); }
+
+static int g_gn_version = -1;   // DORPATCH_GN: v2 (default, cluster per sample), v3 (streaming two-phase; measured slower), v1, twopass
 static int gn_version() {
   if (g_gn_version < 0) {
     const char* e = getenv("DORPATCH_GN");
-    g_gn_version = (e && strcmp(e, "v1") == 0) ? 1 : ((e && strcmp(e, "twopass") == 0) ? 0 : 2);
+    g_gn_version = (e && strcmp(e, "v1") == 0) ? 1 : ((e && strcmp(e, "twopass") == 0) ? 0 : ((e && strcmp(e, "v3") == 0) ? 3 : 2));
   }
   return g_gn_version;
 }
@@ -1638,6 +1996,76 @@ static bool gn2_plan_bwd(int P, int C, size_t es, gn2::Plan* pl) {
   return true;
 }
 
+static int gn3_group(size_t sample_bytes, int streams, int N) {
+  static const size_t l2mb = (size_t)gn2_env("DORPATCH_GN3_L2MB", 24);
+  size_t g = (l2mb << 20) / (sample_bytes * (size_t)streams);
+  if (g < 1) g = 1;
+  if (g > (size_t)N) g = (size_t)N;
+  return (int)g;
+}
+template <typename K>
+static int gn3_grid(K kernel, int total_items) {
+  static std::map<const void*, int> cache;
+  const void* key = (const void*)kernel;
+  auto it = cache.find(key);
+  int per_sm;
+  if (it == cache.end()) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, gn3::TH, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+    cache[key] = per_sm;
+  } else per_sm = it->second;
+  if (g_num_sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int cap = g_num_sms * per_sm;
+  return total_items < cap ? total_items : cap;
+}
+// workspace (floats): partial [N][tiles][64] | m12 [N][64] | ctl (uint32) [32 + 2N]
+static bool gn3_workspace(float* ws, int N, int tiles, float** partial, float** m12, unsigned** ctl) {
+  if ((size_t)N * tiles * 64 + (size_t)N * 64 + 32 + 2 * (size_t)N > (size_t)N * GN_WS_FLOATS_PER_SAMPLE + GN_WS_FLOATS_EXTRA) return false;
+  *partial = ws;
+  *m12 = ws + (size_t)N * tiles * 64;
+  *ctl = reinterpret_cast<unsigned*>(*m12 + (size_t)N * 64);
+  return true;
+}
+static bool launch_gn3_forward(const void* x, void* y, const float* gamma, const float* beta, float* ws, float* stats, int N, int P,
+                               int C, bool bf16, cudaStream_t st) {
+  const size_t es = bf16 ? 2 : 4;
+  const int V = (int)(16 / es), cols = C / V;
+  if (ws == nullptr || cols > gn3::TH || gn3::TH % cols != 0) return false;
+  static const int iter = gn2_env("DORPATCH_GN3_ITER", 16);
+  const int ITER = iter == 8 ? 8 : 16;
+  const size_t sample_vecs = (size_t)P * cols;
+  const int tiles = (int)((sample_vecs + (size_t)gn3::TH * ITER - 1) / ((size_t)gn3::TH * ITER));
+  float *partial, *m12; unsigned* ctl;
+  if (!gn3_workspace(ws, N, tiles, &partial, &m12, &ctl)) return false;
+  const int G = gn3_group(sample_vecs * 16, 1, N);
+  cudaMemsetAsync(ctl, 0, (size_t)(gn3::CTL_WORDS + 2 * N) * 4, st);
+  const int total = 2 * N * tiles;
+#define GN3F(TT, IT) gn3::fwd_kernel<TT, IT><<<gn3_grid(gn3::fwd_kernel<TT, IT>, total), gn3::TH, 0, st>>>((const TT*)x, (TT*)y, gamma, beta, stats, partial, ctl, N, P, C, G, tiles)
+  if (bf16) { if (ITER == 8) GN3F(__nv_bfloat16, 8); else GN3F(__nv_bfloat16, 16); }
+  else { if (ITER == 8) GN3F(float, 8); else GN3F(float, 16); }
+#undef GN3F
+  return cudaPeekAtLastError() == cudaSuccess;
+}
+static bool launch_gn3_backward(const void* dy, const void* x, const void* addend, void* dx, const float* gamma, const float* beta,
+                                const float* stats, float* ws, int N, int P, int C, bool bf16, bool gamma_pos, cudaStream_t st) {
+  const size_t es = bf16 ? 2 : 4;
+  const int V = (int)(16 / es), cols = C / V;
+  if (ws == nullptr || cols > gn3::TH || gn3::TH % cols != 0) return false;
+  constexpr int ITER = 8;
+  const size_t sample_vecs = (size_t)P * cols;
+  const int tiles = (int)((sample_vecs + (size_t)gn3::TH * ITER - 1) / ((size_t)gn3::TH * ITER));
+  float *partial, *m12; unsigned* ctl;
+  if (!gn3_workspace(ws, N, tiles, &partial, &m12, &ctl)) return false;
+  const int G = gn3_group(sample_vecs * 16, 2, N);
+  cudaMemsetAsync(ctl, 0, (size_t)(gn3::CTL_WORDS + 2 * N) * 4, st);
+  const int total = 2 * N * tiles;
+  const bool neg = bf16 ? !gamma_pos : true;
+#define GN3B(TT, NEG) gn3::bwd_kernel<TT, ITER, NEG><<<gn3_grid(gn3::bwd_kernel<TT, ITER, NEG>, total), gn3::TH, 0, st>>>((const TT*)dy, (const TT*)x, (const TT*)addend, (TT*)dx, gamma, beta, stats, partial, m12, ctl, N, P, C, G, tiles)
+  if (bf16) { if (neg) GN3B(__nv_bfloat16, true); else GN3B(__nv_bfloat16, false); }
+  else GN3B(float, true);
+#undef GN3B
+  return cudaPeekAtLastError() == cudaSuccess;
+}
+
 static bool launch_gn2_forward(const void* x, void* y, const float* gamma, const float* beta, float* stats, int N, int P,
                                int C, bool bf16, cudaStream_t st) {
   gn2::Plan pl;
@@ -1669,7 +2097,8 @@ static bool launch_gn2_backward(const void* dy, const void* x, const void* adden
 
 void launch_gn_relu_forward(const void* x, void* y, const float* gamma, const float* beta, float* partial,
                             float* stats, int N, int P, int C, bool bf16, cudaStream_t st) {
-  if (gn_version() == 2 && launch_gn2_forward(x, y, gamma, beta, stats, N, P, C, bf16, st)) return;
+  if (gn_version() == 3 && launch_gn3_forward(x, y, gamma, beta, partial, stats, N, P, C, bf16, st)) return;
+  if (gn_version() >= 2 && launch_gn2_forward(x, y, gamma, beta, stats, N, P, C, bf16, st)) return;
   GnPlan pl;
   if (gn_version() >= 1 && gn_plan(P, C, bf16 ? 2 : 4, &pl)) {
     const int grid = gn_grid(pl, N);
@@ -1685,7 +2114,8 @@ void launch_gn_relu_forward(const void* x, void* y, const float* gamma, const fl
 void launch_gn_relu_backward(const void* dy, const void* x, const void* addend, void* dx, const float* gamma,
                              const float* beta, const float* stats, float* partial, int N, int P, int C, bool bf16,
                              cudaStream_t st, bool gamma_pos) {
-  if (gn_version() == 2 && launch_gn2_backward(dy, x, addend, dx, gamma, beta, stats, N, P, C, bf16, gamma_pos, st)) return;
+  if (gn_version() == 3 && launch_gn3_backward(dy, x, addend, dx, gamma, beta, stats, partial, N, P, C, bf16, gamma_pos, st)) return;
+  if (gn_version() >= 2 && launch_gn2_backward(dy, x, addend, dx, gamma, beta, stats, N, P, C, bf16, gamma_pos, st)) return;
   GnPlan pl;
   const bool ug = (C / GN_GROUPS) >= (bf16 ? 8 : 4);
   if (gn_version() >= 1) {   // both slabs in shared memory when they fit (DORPATCH_GN_DYSMEM=0 disables)

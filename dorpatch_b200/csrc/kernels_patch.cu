@@ -773,4 +773,39 @@ void launch_window_sum(const float* t, float* out, int B, int H, int W, int k, b
   window_sum_kernel<<<dim3((NG + 127) / 128, B), 128, 0, st>>>(t, out, H, W, k, square ? 1 : 0);
 }
 
+// =====================================================================================
+// Failed-mask set on the device (attack.py:259-267): per image a bitmap over the mask universe.
+// One step's update: the first nff[b] sampled indices came from the failed set -- those whose sample now succeeds
+// (loss < thresh) leave it; the remaining indices came from the whole universe -- those whose sample fails join it.
+// Removal is applied before addition (the reference's setdiff1d precedes its unique), then the popcount is returned.
+// One CTA per image; words = ceil(n_mask / 32).
+// =====================================================================================
+__global__ void failed_update_kernel(uint32_t* __restrict__ bits, int words, const int32_t* __restrict__ idx, const float* __restrict__ loss,
+                                     const int32_t* __restrict__ nff, const uint8_t* __restrict__ active, int S, float thresh,
+                                     int32_t* __restrict__ count) {
+  const int b = blockIdx.x;
+  uint32_t* w = bits + (size_t)b * words;
+  __shared__ int red[32];
+  if (active[b]) {
+    const int n_ff = nff[b];
+    for (int s = threadIdx.x; s < n_ff; s += blockDim.x)
+      if (loss[(size_t)b * S + s] < thresh) { const int k = idx[(size_t)b * S + s]; atomicAnd(&w[k >> 5], ~(1u << (k & 31))); }
+    __syncthreads();
+    for (int s = n_ff + threadIdx.x; s < S; s += blockDim.x)
+      if (!(loss[(size_t)b * S + s] < thresh)) { const int k = idx[(size_t)b * S + s]; atomicOr(&w[k >> 5], 1u << (k & 31)); }
+    __syncthreads();
+  }
+  int c = 0;
+  for (int i = threadIdx.x; i < words; i += blockDim.x) c += __popc(w[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i]; count[b] = t; }
+}
+void launch_failed_update(uint32_t* bits, int words, const int32_t* idx, const float* loss, const int32_t* nff, const uint8_t* active,
+                          int B, int S, float thresh, int32_t* count, cudaStream_t st) {
+  failed_update_kernel<<<B, 128, 0, st>>>(bits, words, idx, loss, nff, active, S, thresh, count);
+}
+
 }  // namespace dp

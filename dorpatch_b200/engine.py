@@ -74,6 +74,14 @@ class Engine:
     def launch_count(self):
         return int(self.lib.dp_engine_launch_count(self.handle))
 
+    @property
+    def graph_replays(self):
+        return int(self.lib.dp_engine_graph_replays(self.handle))
+
+    @property
+    def graph_status(self):
+        return self.lib.dp_engine_graph_status(self.handle).decode("utf-8", "replace")
+
     def profile(self, enable=True, reset=False):
         """Per-category CUDA-event profiler of the engine's launches (adds sync overhead)."""
         _lib.check(self.lib.dp_engine_profile(self.handle, 2 if (enable and reset) else (1 if enable else 0)))
@@ -234,6 +242,31 @@ class Engine:
                               clip_max, None, None, host=True)
         _lib.check(self.lib.dp_attack_step_host(self.handle, C.byref(a), C.byref(u), self._stream()))
         return res
+
+    # ------------------------------------------------------------------------------
+    # failed-mask sets on the device (attack.py:96,187-190,259-267)
+    def failed_write(self, b, indices):
+        a, p = _host(np.asarray(indices, dtype=np.int32).reshape(-1), np.int32)
+        _lib.check(self.lib.dp_failed_set_write(self.handle, int(b), p, int(a.size), self._stream()))
+
+    def failed_update(self, idx, nff, active, loss=None, thresh=0.1):
+        """One step of attack.py:259-267 for every image; returns the set sizes [B]."""
+        idx, ip = _host(idx, np.int32)
+        B, S = idx.shape
+        nf, np_ = _host(nff, np.int32)
+        ac, ap = _host(active, np.uint8)
+        lp = None
+        if loss is not None:
+            loss, lp = _host(loss, np.float32)
+        cnt = np.empty(B, np.int32)
+        _lib.check(self.lib.dp_failed_set_update(self.handle, B, S, ip, np_, ap, lp, float(thresh), C.c_void_p(cnt.ctypes.data), self._stream()))
+        return cnt
+
+    def failed_read(self, b, cap=4096):
+        out = np.empty(cap, np.int32)
+        n = C.c_int32()
+        _lib.check(self.lib.dp_failed_set_read(self.handle, int(b), C.c_void_p(out.ctypes.data), cap, C.cast(C.byref(n), C.c_void_p), self._stream()))
+        return out[:n.value].tolist()
 
     # ------------------------------------------------------------------------------
     def net_forward_backward(self, z, dlogits=None):

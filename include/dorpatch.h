@@ -73,6 +73,11 @@ int32_t dp_engine_load_weights(dp_engine* e, int32_t n_tensors, const char* cons
 int64_t dp_engine_device_bytes(const dp_engine* e);
 /* number of CUDA kernels / library launches issued by the engine since create */
 int64_t dp_engine_launch_count(const dp_engine* e);
+/* number of dp_attack_grad calls served by replaying a captured CUDA graph (the launch count above still counts the
+ * kernels each replay executes) */
+int64_t dp_engine_graph_replays(const dp_engine* e);
+/* empty, or why the last graph capture was abandoned (the call then ran as ordinary launches) */
+const char* dp_engine_graph_status(const dp_engine* e);
 
 /* Per-kernel-category profiler: CUDA events around every launch the engine issues.
  * enable: 0 off, 1 on, 2 on + reset counters.  Read returns accumulated device ms, the
@@ -187,6 +192,18 @@ int32_t dp_attack_step_host(dp_engine* e, const dp_attack_args* g, const dp_upda
  * fp32 dev; if dlogits_dev != NULL also writes dz_dev [N,3,H,W] fp32 (d/dz). */
 int32_t dp_net_forward_backward(dp_engine* e, const float* z, int32_t N, float* logits_dev,
                                 const float* dlogits_dev, float* dz_dev, void* stream);
+
+/* ---- failed-mask sets on the device (attack.py:96 `failed_idxs`, :187-190 scan, :259-267 per-step update) --------
+ * One bitmap over the mask universe per image, owned by the engine.  dp_failed_set_write replaces image b's set (the
+ * result of a universe scan); dp_failed_set_update applies one step -- idx_host [B*S] sampled mask indices, the first
+ * nff_host[b] of image b drawn from its failed set, loss < thresh = success; loss_host NULL = use the CW losses the last
+ * dp_attack_grad left on the device -- and returns the set sizes count_host[B] (all the bookkeeping of attack.py:269-308
+ * needs); dp_failed_set_read returns the sorted indices (needed only when the sampler draws from the set, i >= 1000). */
+int32_t dp_failed_set_write(dp_engine* e, int32_t b, const int32_t* idx_host, int32_t n, void* stream);
+int32_t dp_failed_set_update(dp_engine* e, int32_t B, int32_t S, const int32_t* idx_host, const int32_t* nff_host,
+                             const uint8_t* active_host, const float* loss_host, float thresh, int32_t* count_host,
+                             void* stream);
+int32_t dp_failed_set_read(dp_engine* e, int32_t b, int32_t* idx_host_out, int32_t cap, int32_t* n_out, void* stream);
 
 /* Op-level hooks for the parity tests (tests/test_gpu_ops.py); not part of the reference-facing surface.
  * dp_debug_stem_bwd_reduce: the bf16 engine's fused stem-dgrad + masked EOT reduce (K1^T as the bench runs it) on a

@@ -346,3 +346,35 @@ def test_two_lane_chunk_overlap_is_bit_identical(oracle_params, precision):
     os.environ.pop("DORPATCH_LANES", None)
     assert torch.equal(out["1"][0], out["2"][0])
     assert np.array_equal(out["1"][1], out["2"][1]) and np.array_equal(out["1"][2], out["2"][2])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cuda_graph_replay_is_bit_identical(oracle_params, precision):
+    """dp_attack_grad captures its launch sequence into a CUDA graph on the second call of a signature and replays it
+    afterwards.  Same kernels, same order, fresh staging contents per call: every call must equal the
+    eager engine (DORPATCH_GRAPH=0) bit for bit, including calls whose rectangles / labels differ from the captured one."""
+    import os
+    from dorpatch_b200.engine import Engine
+    H, B, S = 112, 3, 4                       # chunk 4 -> 3 chunks on two lanes
+    x, m, p = _rand((B, 3, H, H), 91), _rand((B, 1, H, H), 92), _rand((B, 3, H, H), 93)
+    calls = [(_rects_for(H, np.random.RandomState(10 + k).randint(0, 2520, (B, S)), 2), np.array([1 + k, 2, 3 + 5 * k])) for k in range(4)]
+    out = {}
+    for graph in ("0", "1"):
+        os.environ["DORPATCH_GRAPH"] = graph
+        e = Engine(img=H, precision=precision, chunk=4, max_images=B, autotune=False)
+        e.load_state_dict(oracle_params)
+        xd, md, pd = x.to(DEV), m.to(DEV), p.to(DEV)
+        G = torch.zeros(B, 3, H, H, device=DEV)
+        res = []
+        for rects, y in calls:
+            r = e.attack_grad(xd, md, pd, rects, y, [True, False, True], 0.1, 4.0, 0, G)
+            torch.cuda.synchronize()
+            res.append((G.cpu().clone(), r["loss_adv"].copy(), r["preds"].copy(), r["group_lasso"].copy()))
+        out[graph] = res
+        replays, why = e.graph_replays, e.graph_status
+        e.close()
+        assert replays == (3 if graph == "1" else 0), (replays, why)        # call 1 eager, call 2 capture + launch, calls 3-4 replay
+    os.environ.pop("DORPATCH_GRAPH", None)
+    for a, b in zip(out["0"], out["1"]):
+        assert torch.equal(a[0], b[0])
+        assert all(np.array_equal(u, v) for u, v in zip(a[1:], b[1:]))

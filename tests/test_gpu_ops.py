@@ -103,8 +103,9 @@ def test_bf16_stem_bwd_reduce_vs_torch_fp32(engines, oracle_params, B, S):
     idx = np.random.RandomState(7).randint(0, 2520, (B, S))
     rects = PM.gather(PM.universe(H, 2), idx)
     G = torch.empty(B, 3, H, H, device=DEV)
-    _lib.check(e.lib.dp_debug_stem_bwd_reduce(e.handle, _ptr(dY.to(DEV)), C.c_void_p(np.ascontiguousarray(rects.reshape(N, 4, 4), np.int16).ctypes.data),
-                                              B, S, _ptr(G), e._stream()))
+    dYd = dY.to(DEV)
+    rects_c = np.ascontiguousarray(rects.reshape(N, 4, 4), np.int16)
+    _lib.check(e.lib.dp_debug_stem_bwd_reduce(e.handle, _ptr(dYd), C.c_void_p(rects_c.ctypes.data), B, S, _ptr(G), e._stream()))
     torch.cuda.synchronize()
     w = OR.standardize(oracle_params["stem.conv.weight"]).to(torch.bfloat16).float()         # [64,3,7,7]
     dX = F.conv_transpose2d(dY.float().permute(0, 3, 1, 2), w, stride=2, padding=3, output_padding=1)   # [N,3,224,224]
@@ -149,8 +150,10 @@ def test_tcgen05_gn_gemm_vs_fp32(engines, N, P, K, Nout, shortcut):
     if shortcut:
         ref = ref + r.float()
     out = torch.empty(M, Nout, dtype=torch.bfloat16, device=DEV)
-    _lib.check(e.lib.dp_debug_gn_gemm(e.handle, _ptr(x.to(DEV)), _ptr(w.to(DEV)), _ptr(stats.to(DEV)), _ptr(gamma.to(DEV)), _ptr(beta.to(DEV)),
-                                      _ptr(r.to(DEV)) if shortcut else None, _ptr(out), N, P, K, Nout, e._stream()))
+    xd, wd, sd, gd, bd = x.to(DEV), w.to(DEV), stats.to(DEV), gamma.to(DEV), beta.to(DEV)     # keep the device copies alive
+    rd = r.to(DEV) if shortcut else None
+    _lib.check(e.lib.dp_debug_gn_gemm(e.handle, _ptr(xd), _ptr(wd), _ptr(sd), _ptr(gd), _ptr(bd), _ptr(rd), _ptr(out), N, P, K, Nout,
+                                      e._stream()))
     torch.cuda.synchronize()
     got = out.cpu().float()
     assert torch.isfinite(got).all()
@@ -158,3 +161,40 @@ def test_tcgen05_gn_gemm_vs_fp32(engines, N, P, K, Nout, shortcut):
     rel = float((got - ref).norm() / ref.norm())
     print("gn_gemm N=%d P=%d K=%d Nout=%d: max abs / max %.2e, rel L2 %.2e" % (N, P, K, Nout, mx, rel))
     assert mx <= 1.0 / 128 and rel <= 4e-3, (mx, rel)
+
+
+def test_device_failed_set_equals_host_state_machine(engines):
+    """The failed-mask set kept as a device bitmap (dp_failed_set_write / _update / _read) against the host
+    list arithmetic of attack.py:259-267 (np.setdiff1d / np.unique) driven by the same sampler over 400 random steps of two
+    images: identical set sizes every step, identical sorted contents whenever the sampler reads them, identical samples."""
+    from dorpatch_b200.attack import _ImageState
+    e = engines("fp32")
+    B, S, n_mask = 2, 8, 2520
+    host = [_ImageState(0.01, 1e-3, 3, False, np.random.RandomState(10 + b)) for b in range(B)]
+    dev = [_ImageState(0.01, 1e-3, 3, False, np.random.RandomState(10 + b)) for b in range(B)]
+    for b, s in enumerate(dev):
+        s.dev = (e, b)
+    rng = np.random.RandomState(0)
+    for b in range(B):
+        init = sorted(rng.choice(n_mask, 40, replace=False).tolist())
+        host[b].failed, host[b].n_failed = list(init), len(init)
+        dev[b].set_failed(init)
+    for i in range(990, 1390):                       # crosses i == 1000, where half of the samples start to come from the set
+        idx_h, idx_d, nff_h, nff_d = [], [], [], []
+        for b in range(B):
+            a, na = host[b].sample(i, n_mask, S)
+            c, nc = dev[b].sample(i, n_mask, S)
+            assert na == nc and np.array_equal(a, c)
+            idx_h.append(a); nff_h.append(na); idx_d.append(c); nff_d.append(nc)
+        loss = (rng.rand(B, S) < 0.6).astype(np.float32) * 0.5
+        counts = e.failed_update(np.stack(idx_d), nff_d, [True] * B, loss=loss)
+        for b in range(B):
+            ra = host[b].bookkeeping(1, i, loss[b], idx_h[b], nff_h[b], 1.0)
+            rb = dev[b].bookkeeping(1, i, loss[b], idx_d[b], nff_d[b], 1.0, n_failed=counts[b])
+            assert ra == rb and host[b].n_failed == dev[b].n_failed == counts[b]
+            assert (host[b].lr, host[b].structured, host[b].not_decay, host[b].num_failure) == (dev[b].lr, dev[b].structured, dev[b].not_decay, dev[b].num_failure)
+        if i % 50 == 0:
+            for b in range(B):
+                assert e.failed_read(b) == host[b].failed
+    inactive = e.failed_update(np.zeros((B, S), np.int32), [0] * B, [False] * B, loss=np.ones((B, S), np.float32))
+    assert [int(v) for v in inactive] == [host[b].n_failed for b in range(B)]      # inactive images are left untouched

@@ -46,7 +46,7 @@ static void run_shape(int N, int P, int C, bool bf16, bool negative_gamma) {
   CK(cudaMalloc(&x, bytes * R)); CK(cudaMalloc(&dy, bytes * R)); CK(cudaMalloc(&ad, bytes * R));
   CK(cudaMalloc(&y, bytes * R)); CK(cudaMalloc(&dx, bytes * R));
   CK(cudaMalloc(&ga, C * 4)); CK(cudaMalloc(&be, C * 4)); CK(cudaMalloc(&stats, (size_t)N * 64 * 4));
-  CK(cudaMalloc(&partial, (size_t)N * dp::GN_MAX_SPLITS * 64 * 4));
+  CK(cudaMalloc(&partial, ((size_t)N * dp::GN_WS_FLOATS_PER_SAMPLE + dp::GN_WS_FLOATS_EXTRA) * 4));
   for (int r = 0; r < R; ++r) {
     CK(cudaMemcpy((char*)x + bytes * r, hx.data(), bytes, cudaMemcpyHostToDevice));
     CK(cudaMemcpy((char*)dy + bytes * r, hdy.data(), bytes, cudaMemcpyHostToDevice));
@@ -110,6 +110,28 @@ static void run_shape(int N, int P, int C, bool bf16, bool negative_gamma) {
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
     return ms / reps;
   };
+  if (getenv("GNBENCH_TRACE")) {   // phase attribution of the v2 forward kernel: mean cycles between the stamps over all CTAs
+    const size_t max_ctas = (size_t)N * 16;
+    unsigned long long* tr; CK(cudaMalloc(&tr, max_ctas * 8 * 8)); CK(cudaMemset(tr, 0, max_ctas * 8 * 8));
+    for (int r = 0; r < R; ++r) fwd(r);
+    CK(cudaStreamSynchronize(st));
+    dp::gn2_set_trace(tr);
+    fwd(0);
+    CK(cudaStreamSynchronize(st));
+    dp::gn2_set_trace(nullptr);
+    std::vector<unsigned long long> h(max_ctas * 8);
+    CK(cudaMemcpy(h.data(), tr, max_ctas * 8 * 8, cudaMemcpyDeviceToHost));
+    double d[7] = {0, 0, 0, 0, 0, 0, 0}; size_t cnt = 0;
+    unsigned long long tmin = ~0ull, tmax = 0;
+    for (size_t c = 0; c < max_ctas; ++c) {
+      if (h[c * 8 + 7] == 0) continue;
+      for (int i = 0; i < 7; ++i) d[i] += (double)((long long)h[c * 8 + i + 1] - (long long)h[c * 8 + i]);
+      ++cnt;
+    }
+    if (cnt) printf("  trace (%zu CTAs, mean cycles): load+stats, thread 0 %.0f | slowest warp later by %.0f | cta-reduce %.0f | cluster.sync %.0f | finalize %.0f | apply+store %.0f | exit-wait %.0f | total %.0f\n",
+                    cnt, d[0] / cnt, d[1] / cnt, d[2] / cnt, d[3] / cnt, d[4] / cnt, d[5] / cnt, d[6] / cnt, (d[0] + d[1] + d[2] + d[3] + d[4] + d[5] + d[6]) / cnt);
+    cudaFree(tr);
+  }
   const float tf = time_it([&](int r) { fwd(r); });
   const float tb = time_it([&](int r) { bwd(r, false); });
   const float tba = time_it([&](int r) { bwd(r, true); });

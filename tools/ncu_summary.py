@@ -19,6 +19,17 @@ WANT = [
     ("launch__cluster_size", "cluster"),
     ("launch__shared_mem_per_block_dynamic", "dyn_smem"),
     ("smsp__inst_executed.sum", "warp_insts"),
+    ("sm__inst_executed.avg.per_cycle_elapsed", "ipc_per_sm"),
+    ("smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "stall_long_scoreboard"),
+    ("smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio", "stall_short_scoreboard"),
+    ("smsp__average_warp_latency_issue_stalled_barrier.ratio", "stall_barrier"),
+    ("smsp__average_warp_latency_issue_stalled_membar.ratio", "stall_membar"),
+    ("smsp__average_warp_latency_issue_stalled_wait.ratio", "stall_wait"),
+    ("smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio", "stall_math_throttle"),
+    ("smsp__average_warp_latency_issue_stalled_lg_throttle.ratio", "stall_lg_throttle"),
+    ("smsp__average_warp_latency_issue_stalled_not_selected.ratio", "stall_not_selected"),
+    ("smsp__average_warp_latency_issue_stalled_sleeping.ratio", "stall_sleeping"),
+    ("smsp__average_warp_latency_issue_stalled_no_instruction.ratio", "stall_no_instruction"),
 ]
 
 
