@@ -168,6 +168,17 @@ def _dist():
     return None
 
 
+def _assert_same_on_all_ranks(dist, arr, device, what):
+    """Cheap consistency check of host-side state that EOT sharding assumes identical on every rank."""
+    a = np.ascontiguousarray(arr).astype(np.int64).ravel()
+    chk = torch.tensor([int(a.sum()), int((a * (np.arange(a.size) % 8191 + 1)).sum())], dtype=torch.int64, device=device)
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if not torch.equal(lo, hi):
+        raise RuntimeError("ranks disagree on %s: seed every rank identically (utils.set_random_seed) before generate()" % what)
+
+
 def exchange_shards(dist, G, loss_adv, preds):
     """The only cross-rank exchange of a step: SUM all-reduce of the patch gradient G
     [B,3,H,W] (each rank holds the sum over ITS S/world samples, already divided by the global
@@ -262,6 +273,10 @@ class DorPatch(object):
             mp = [(torch.rand([1, 1, H, W], generator=g), torch.rand([1, 3, H, W], generator=g)) for g in gens]
             adv_mask = torch.cat([m for m, _ in mp]).to(dev)
             adv_pattern = torch.cat([q for _, q in mp]).to(dev)
+        if dist:
+            # EOT sharding needs bit-identical patch state on every rank: rank 0's draw is authoritative
+            dist.broadcast(adv_mask, 0)
+            dist.broadcast(adv_pattern, 0)
         mask_best = torch.zeros_like(adv_mask)
         pattern_best = torch.zeros_like(adv_pattern)
         if y is None:                                            # attack.py:67-69
@@ -368,6 +383,10 @@ class DorPatch(object):
                         idx[b], nff[b] = s.sample(i, n_mask, S)
                         if dual:
                             idx2[b], _ = s.sample(i, n_mask, S)
+                if dist and i % 100 == 0:
+                    # every rank must have drawn the same indices (same RNG streams): a diverged rank would evaluate a
+                    # slice of a different sample set and the gathered losses would be book-kept against the wrong masks
+                    _assert_same_on_all_ranks(dist, idx, dev, "EOT sample indices at step %d" % i)
                 sl = slice(rank * S_loc, (rank + 1) * S_loc)
                 rects = _masks.gather(table, idx[:, sl], idx2[:, sl] if dual else None)
                 structured_used = [s.structured for s in st]

@@ -232,6 +232,7 @@ struct dp_engine {
   typedef std::tuple<int, int, int, int, const void*, const void*, const void*, const void*, float, float, int> GraphKey;
   std::map<GraphKey, GraphEnt> graphs;
   bool graphs_on = true;
+  cudaStream_t cap_stream = nullptr;   // capture happens here when the caller's stream is the legacy / per-thread default stream (not capturable)
   int64_t graph_replays = 0;
   std::string graph_msg;               // why the last capture attempt was abandoned (diagnostics)
   void drop_graphs() {
@@ -348,6 +349,7 @@ struct dp_engine {
     if (n_lanes > 2) n_lanes = 2;
     lanes.resize(n_lanes);
     CUDA_OK(cudaEventCreateWithFlags(&ev_prep, cudaEventDisableTiming));
+    CUDA_OK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
     for (int l = 0; l < n_lanes; ++l) {
       LaneBufs& L = lanes[l];
       for (auto& b : blocks) {
@@ -882,6 +884,7 @@ void dp_engine_destroy(dp_engine* e) {
   }
   if (!e->lanes.empty()) e->cudnn = e->lanes[0].cudnn;
   if (e->ev_prep) cudaEventDestroy(e->ev_prep);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   for (void* p : e->allocs) cudaFree(p);
   if (e->pin) cudaFreeHost(e->pin);
   if (e->cudnn) cudnnDestroy(e->cudnn);
@@ -1172,12 +1175,16 @@ static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t
     } else if (!ent.failed && ent.calls >= 2) {          // call 1 ran eagerly: every plan / algorithm choice exists now
       const int64_t l0 = e->launches;
       cudaGraph_t graph = nullptr;
-      bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      // the legacy / per-thread default streams (PyTorch's default current stream) cannot be captured: record the
+      // sequence on an engine-owned stream instead; the instantiated graph launches on the caller's stream either way
+      cudaStream_t cs = (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) ? e->cap_stream : st;
+      const cudaError_t cb = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+      bool ok = cb == cudaSuccess;
       if (ok) {
-        try { attack_grad_enqueue(e, a, L_, st); } catch (const std::exception& ex) { ok = false; e->graph_msg = std::string("enqueue: ") + ex.what(); }
-        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        try { attack_grad_enqueue(e, a, L_, cs); } catch (const std::exception& ex) { ok = false; e->graph_msg = std::string("enqueue: ") + ex.what(); }
+        const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
         if (ce != cudaSuccess || graph == nullptr) { if (ok) e->graph_msg = std::string("end capture: ") + cudaGetErrorString(ce); ok = false; }
-      } else e->graph_msg = "begin capture failed";
+      } else e->graph_msg = std::string("begin capture: ") + cudaGetErrorString(cb);
       if (ok) {
         const cudaError_t ci = cudaGraphInstantiate(&ent.exec, graph, 0);
         if (ci != cudaSuccess) { ok = false; ent.exec = nullptr; e->graph_msg = std::string("instantiate: ") + cudaGetErrorString(ci); }

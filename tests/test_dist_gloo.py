@@ -89,3 +89,38 @@ def test_universe_scan_is_sharded_by_mask_index_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _consistency_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dorpatch_b200.attack import _assert_same_on_all_ranks
+    idx = np.random.RandomState(3).randint(0, 2520, (4, 16))
+    _assert_same_on_all_ranks(dist, idx, "cpu", "identical indices")          # must pass
+    bad = idx.copy()
+    if rank == 1:
+        bad[2, 5], bad[2, 6] = bad[2, 6], bad[2, 5]                             # same multiset, different order
+    try:
+        _assert_same_on_all_ranks(dist, bad, "cpu", "diverged indices")
+        raised = False
+    except RuntimeError:
+        raised = True
+    q.put((rank, raised))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rank_divergence_of_sample_indices_is_detected_world2():
+    """EOT sharding assumes every rank drew the same sample indices; a rank with another RNG state must be caught
+    (on every rank, so that no rank is left waiting in a collective)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_consistency_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
