@@ -208,6 +208,7 @@ class Workload:
         self.states = [_ImageState(0.01, 1e-3, y[b], c["targeted"], np.random.RandomState(1234 + b)) for b in range(B)]
         self.PM = PM
         self.nff0, self.act1 = np.zeros(B, np.int32), np.ones(B, np.uint8)
+        self.host_s = 0.0
         self.hx = torch.empty(self.x.shape, pin_memory=True).copy_(self.x)
         self.hm = torch.empty(self.mask.shape, pin_memory=True).copy_(self.mask)
         self.hp = torch.empty(self.pattern.shape, pin_memory=True).copy_(self.pattern)
@@ -224,10 +225,10 @@ class Workload:
 
     def finish(self, i, idx, r, G):
         import torch
-        loss_adv = r["loss_adv"]
+        loss_adv, work = r["loss_adv"], None
         if self.world > 1:
             from dorpatch_b200.attack import exchange_shards
-            loss_adv, _ = exchange_shards(self.dist, G, loss_adv, r["preds"])
+            loss_adv, _, work = exchange_shards(self.dist, G, loss_adv, r["preds"], defer=True)   # all-reduce under the bookkeeping
         target = r["group_lasso"] if self.stage == 0 else r["loss_struc"]
         st_used = [s.structured for s in self.states]
         cg_used = [s.coeff_group_lasso for s in self.states]
@@ -235,12 +236,18 @@ class Workload:
         counts = self.eng.failed_update(idx, self.nff0, self.act1, loss=loss_adv if self.world > 1 else None)
         for b, s in enumerate(self.states):
             s.bookkeeping(self.stage, i, loss_adv[b], idx[b], 0, target[b], n_failed=counts[b])
+        if work is not None:
+            work.wait()                                   # orders the sign step after the all-reduce (stream dependency, no host block)
         return np.full(self.B, 0.01, np.float32), st_used, cg_used
 
     def step(self, i):
+        t0 = time.perf_counter()
         idx, rects = self.host_sample(i)
+        self.host_s += time.perf_counter() - t0               # host time the GPU waits for (RNG-exact sampling, rectangle gather)
         r = self.eng.attack_grad(self.x, self.mask, self.pattern, rects, self.y, self.crit, 0.1, 4.0, self.stage, self.G, S_total=self.S)
+        t0 = time.perf_counter()
         lr, st_used, cg_used = self.finish(i, idx, r, self.G)
+        self.host_s += time.perf_counter() - t0               # exchange + bookkeeping (the all-reduce runs under it)
         self.eng.attack_update(self.x, self.mask, self.pattern, self.G, lr, st_used, cg_used, 1e-3, self.stage)
 
     def step_e2e(self, i):
@@ -335,9 +342,11 @@ def run_native(args):
         if sampler is not None:
             sampler.start()
             time.sleep(0.3)
+        wl.host_s = 0.0
         ms, launches = timed(eng, wl.step, K, W)
         clocks = sampler.stop() if sampler is not None else None
-        res = dict(value=wl.samples_per_step * K / (ms / 1e3), ms_per_step=ms / K, launches=int(launches), clocks=clocks, wl=wl, eng=eng)
+        res = dict(value=wl.samples_per_step * K / (ms / 1e3), ms_per_step=ms / K, launches=int(launches), clocks=clocks, wl=wl, eng=eng,
+                   host_ms=wl.host_s / K * 1e3, graph_replays=eng.graph_replays)
         if e2e:
             for i in range(2):
                 wl.step_e2e(W + K + i)
@@ -366,6 +375,7 @@ def run_native(args):
         "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic", "config": workload_config(args.config, world),
         "clocks": head["clocks"], "gpu_launches": head["launches"],
+        "host_ms_per_step": head["host_ms"], "graph_replays": head["graph_replays"],
         "e2e": {"value": head["e2e_value"], "unit": UNIT, "ms_per_step": head["e2e_ms"], "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h,
                 "path": "dp_attack_step_host (C ABI, host buffers)" if world == 1 else "pinned host -> H2D -> grad/allreduce/update -> D2H"},
@@ -404,11 +414,11 @@ def run_native(args):
         import ctypes as C
         from dorpatch_b200 import _lib
         B, S_loc = wl.B, wl.S_loc
-        n_chunk = min(args.chunk, B * S_loc)
+        n_chunk = int(eng.lib.dp_k1_samples_per_launch(eng.handle, B * S_loc))       # what ONE K1 launch of the step covers
         rects_all = wl.PM.gather(wl.table, np.stack([np.random.RandomState(b).choice(wl.n_mask, S_loc, replace=False) for b in range(B)]))
         ra_dev = torch.from_numpy(np.ascontiguousarray(rects_all.reshape(B * S_loc, 4, 4), np.int16)).to(dev)
         dt_t = torch.bfloat16 if es == 2 else torch.float32
-        n_rot = max(2, int(400e6 // (n_chunk * IMG * IMG * eng.c_pad * es)) + 1)      # rotate over > 400 MB of outputs
+        n_rot = max(2, int(400e6 // (n_chunk * IMG * IMG * eng.c_pad * es)) + 1)      # rotate over > 400 MB of outputs (> L2)
         bufs = [torch.empty((n_chunk, IMG, IMG, eng.c_pad), dtype=dt_t, device=dev) for _ in range(n_rot)]
         eng.paste(wl.x, wl.mask, wl.pattern, 4.0)                                 # the clip scale the fused variant reads
         n_starts = list(range(0, B * S_loc - n_chunk + 1, n_chunk)) or [0]
@@ -446,7 +456,10 @@ def run_native(args):
             tj = json.load(open(tpath))
             if tj.get("samples") == n_chunk and tj.get("dtype") == args.precision:
                 traffic, tnote = tj.get("dram_bytes"), tj.get("note")
-        out["roofline"] = {"kernel": "expand_kernel<FUSED=1> (K1: paste + L2-scale + normalise + occlude, TMA bulk tiles), the in-step variant",
+        phys_bytes = n_chunk * IMG * IMG * eng.c_pad * es + img_in_launch * 7 * IMG * IMG * 4
+        out["roofline"] = {"kernel": "expand_kernel<FUSED=1> (K1: paste + L2-scale + normalise + occlude, TMA bulk tiles), the in-step variant and launch shape (%d samples per launch)" % n_chunk,
+                           "physical_bytes_per_launch": phys_bytes, "frac_physical": phys_bytes / k1_ms / 1e6 / pk["hbm"],
+                           "physical_note": "bytes the launch really moves: the network input is [N,H,W,%d] (channel pad %d -> %d for the library stem)" % (eng.c_pad, 3, eng.c_pad) if eng.c_pad != 3 else "tight C=3 layout: physical == algorithmic",
                            "bound": "hbm", "achieved": alg_bytes / k1_ms / 1e6, "peak": pk["hbm"], "unit": "GB/s",
                            "frac": alg_bytes / k1_ms / 1e6 / pk["hbm"], "traffic": traffic, "traffic_note": tnote,
                            "ms": k1_ms, "ms_single_launch_event_pair": k1_ms_single, "samples_per_launch": n_chunk,
@@ -511,7 +524,7 @@ def run_native(args):
                 continue
             try:
                 r = measure(prec, cfg, K2 if cfg != "b1" else 20, e2e=(cfg in ("c2", "c3")))
-                leg = {"value": r["value"], "ms_per_step": r["ms_per_step"], "gpu_launches": r["launches"], "dtype": prec,
+                leg = {"value": r["value"], "ms_per_step": r["ms_per_step"], "gpu_launches": r["launches"], "dtype": prec, "host_ms_per_step": r["host_ms"],
                        "config": workload_config(cfg, 1)["workload"]}
                 if "e2e_value" in r:
                     leg["e2e"] = r["e2e_value"]

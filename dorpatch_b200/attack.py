@@ -179,30 +179,38 @@ def _assert_same_on_all_ranks(dist, arr, device, what):
         raise RuntimeError("ranks disagree on %s: seed every rank identically (utils.set_random_seed) before generate()" % what)
 
 
-def exchange_shards(dist, G, loss_adv, preds):
+def exchange_shards(dist, G, loss_adv, preds, defer=False):
     """The only cross-rank exchange of a step: SUM all-reduce of the patch gradient G
     [B,3,H,W] (each rank holds the sum over ITS S/world samples, already divided by the global
     S) and an all-gather of the per-sample results [B,S/world] -> [B,S] in rank order, so every
-    rank takes the identical bookkeeping decisions and the identical sign step."""
+    rank takes the identical bookkeeping decisions and the identical sign step.
+
+    Order matters for overlap: both collectives run on the process group's one NCCL stream, so the tiny
+    all-gather goes FIRST and its single device->host copy waits for it alone; the large all-reduce
+    (B*0.6 MB) is enqueued behind it asynchronously and runs under the host bookkeeping.  With
+    ``defer=True`` the all-reduce's work handle is returned as a third value and the caller waits on it
+    right before the sign step (``work.wait()`` orders the compute stream after NCCL's; it does not block
+    the host); otherwise the wait happens here."""
     world = dist.get_world_size()
-    # the all-reduce is enqueued first and asynchronously (NCCL's own stream); the small gather and its single
-    # device->host copy run while it is in flight, and the sign step (next on the compute stream) waits for it.
-    work = dist.all_reduce(G, async_op=True)
     s_loc = loss_adv.shape[1]
     pack = torch.from_numpy(np.concatenate([loss_adv, preds.astype(np.float32)], 1))
     if G.is_cuda:
         pack = pack.pin_memory().to(G.device, non_blocking=True)
         allp = torch.empty((world,) + tuple(pack.shape), dtype=pack.dtype, device=G.device)
         dist.all_gather_into_tensor(allp, pack)
+        work = dist.all_reduce(G, async_op=True)
         allp = allp.cpu()                                   # one D2H + one synchronisation for all ranks' results
     else:                                                   # gloo (CPU tests)
         outs = [torch.empty_like(pack) for _ in range(world)]
         dist.all_gather(outs, pack)
+        work = dist.all_reduce(G, async_op=True)
         allp = torch.stack(outs)
-    work.wait()
     allp = allp.numpy()
     loss_all = np.concatenate([allp[r][:, :s_loc] for r in range(world)], 1)
     preds_all = np.concatenate([allp[r][:, s_loc:] for r in range(world)], 1).astype(np.int32)
+    if defer:
+        return loss_all, preds_all, work
+    work.wait()
     return loss_all, preds_all
 
 
@@ -398,8 +406,9 @@ class DorPatch(object):
                 r = eng.attack_grad(x, adv_mask, adv_pattern, rects, [s.y for s in st],
                                     [s.crit_targeted for s in st], confidence, eps, stage, G, S_total=S, xforms=xf)
                 loss_adv, preds = r["loss_adv"], r["preds"]
-                if dist:                                         # one all-reduce of the patch gradient per step
-                    loss_adv, preds = exchange_shards(dist, G, loss_adv, preds)
+                reduce_work = None
+                if dist:                                         # one all-reduce of the patch gradient per step, under the bookkeeping
+                    loss_adv, preds, reduce_work = exchange_shards(dist, G, loss_adv, preds, defer=True)
                 last_preds = preds
                 loss_target = r["group_lasso"] if stage == 0 else r["loss_struc"]
                 counts = None
@@ -427,6 +436,8 @@ class DorPatch(object):
                     else:
                         lr_used[b] = s.lr
                 steps += 1
+                if reduce_work is not None:                      # the sign step (and the stale-gradient capture) need the reduced G
+                    reduce_work.wait()
                 if stage == 0 and stopped_now:                   # capture the gradient the reference leaves in .grad
                     gp_full = torch.empty_like(x)
                     eng.attack_update(x, adv_mask, adv_pattern, G, np.zeros(B, np.float32), structured_used, coeff_used,

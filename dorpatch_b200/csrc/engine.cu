@@ -260,6 +260,26 @@ struct dp_engine {
     pin_bytes = std::max(bytes, (size_t)1 << 20);
     CUDA_OK(cudaMallocHost((void**)&pin, pin_bytes));
   }
+  // K1 for the WHOLE step in one launch (all B*S samples into one buffer, the chunks then read their slices): the launch
+  // shape of one classifier chunk (16 images x 28 row tiles) is too small to fill 148 SMs for more than one ragged wave
+  // (in-step 0.49-0.55 of HBM peak against 0.69 for a 512-sample launch, profiles/README.md).  Bounded by
+  // DORPATCH_K1_WHOLE_MB (default 4096; 0 = one launch per chunk as in round 1).
+  void* net_in_all = nullptr;
+  size_t net_in_all_cap = 0, k1_whole_max = (size_t)4096 << 20;
+  size_t sample_in_bytes() const { return (size_t)H * H * Cp * es; }
+  bool k1_whole_ok(int n) const { return k1_whole_max > 0 && n > chunk && (size_t)n * sample_in_bytes() <= k1_whole_max; }
+  bool ensure_net_in_all(int n) {
+    if (!k1_whole_ok(n)) return false;
+    const size_t bytes = (size_t)n * sample_in_bytes();
+    if (bytes > net_in_all_cap) {
+      drop_graphs();
+      if (net_in_all) { CUDA_OK(cudaFree(net_in_all)); device_bytes -= (int64_t)net_in_all_cap; net_in_all = nullptr; net_in_all_cap = 0; }
+      CUDA_OK(cudaMalloc(&net_in_all, bytes));
+      net_in_all_cap = bytes;
+      device_bytes += (int64_t)bytes;
+    }
+    return true;
+  }
   void ensure_samples(int n) {
     if (n <= cap_samples) return;
     drop_graphs();                       // captured launches hold the old per-sample buffers
@@ -834,6 +854,7 @@ int32_t dp_engine_create(const dp_config* cfg, dp_engine** out) {
     const char* fg_env = getenv("DORPATCH_FUSED_GEMM");
     e->fused_gemm = e->bf16 && fg_env && atoi(fg_env) != 0;   // not validated on hardware yet: off unless asked for
     if (const char* g_env = getenv("DORPATCH_GRAPH")) e->graphs_on = atoi(g_env) != 0;
+    if (const char* k_env = getenv("DORPATCH_K1_WHOLE_MB")) e->k1_whole_max = (size_t)std::max(0, atoi(k_env)) << 20;
     const char* pb_env = getenv("DORPATCH_POOL_BWD");
     // measured: rebuilding the d_stem patch in shared memory costs more than the saved HBM round trip
     // (2.25 ms vs 1.33 + 0.71 ms per 512-sample step) -> off unless DORPATCH_POOL_BWD=fused
@@ -885,6 +906,7 @@ void dp_engine_destroy(dp_engine* e) {
   if (!e->lanes.empty()) e->cudnn = e->lanes[0].cudnn;
   if (e->ev_prep) cudaEventDestroy(e->ev_prep);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  if (e->net_in_all) cudaFree(e->net_in_all);
   for (void* p : e->allocs) cudaFree(p);
   if (e->pin) cudaFreeHost(e->pin);
   if (e->cudnn) cudnnDestroy(e->cudnn);
@@ -1017,6 +1039,11 @@ int32_t dp_expand_step_dev(dp_engine* e, const float* x, const float* mask, cons
   DP_CATCH
 }
 
+int32_t dp_k1_samples_per_launch(const dp_engine* e, int32_t n_samples) {
+  if (!e || n_samples < 1) return 0;
+  return e->k1_whole_ok(n_samples) ? n_samples : std::min(n_samples, e->chunk);
+}
+
 int32_t dp_predict(dp_engine* e, const float* img, int32_t B, int32_t S, const int16_t* rects_host, int32_t* preds_host,
                    float* logits_host, void* stream) {
   DP_TRY
@@ -1083,6 +1110,13 @@ static void attack_grad_enqueue(dp_engine* e, const dp_attack_args* a, const Gra
   // Two lanes: chunks alternate between two workspaces / internal streams (only when every chunk holds whole
   // images, so no two chunks accumulate into the same G[b]).  Everything enqueued so far is on `st`.
   cudaStream_t const user_st = st;
+  // K1 once for the whole step when its output fits the budget (see ensure_net_in_all); the chunks read their slices
+  const bool k1_whole = !xf_bytes && e->net_in_all != nullptr && e->k1_whole_ok(N) && (size_t)N * e->sample_in_bytes() <= e->net_in_all_cap;
+  if (k1_whole) {
+    PROF(e, "expand_k1", (double)N * H * H * 3 * e->es + 7.0 * H * H * 4 * (double)B, 0, st,
+         dp::launch_expand(nullptr, a->x, a->mask, a->pattern, e->scale, rects, e->net_in_all, B, S, 0, N, H, H, e->Cp, e->bf16, true, e->num_sms, st));
+    KERNEL_OK(); ++e->launches;
+  }
   // (the per-category profiler serialises on one lane so that category times do not overlap)
   const bool dual = e->lanes.size() == 2 && N > e->chunk && (e->chunk % S == 0) && !e->prof_on;
   if (dual) {
@@ -1093,15 +1127,19 @@ static void attack_grad_enqueue(dp_engine* e, const dp_attack_args* a, const Gra
   for (int n0 = 0; n0 < N; n0 += e->chunk, ++chunk_id) {
     const int n = std::min(e->chunk, N - n0);
     if (dual) { e->use_lane(chunk_id & 1); st = e->lanes[chunk_id & 1].stream; }
-    if (xf_bytes) {
+    const void* chunk_in = e->net_in;
+    if (k1_whole) {
+      chunk_in = (const char*)e->net_in_all + (size_t)n0 * e->sample_in_bytes();
+    } else if (xf_bytes) {
       PROF(e, "expand_affine", (double)n * H * H * 3 * e->es + 3.0 * H * H * 4 * (double)n / S, 0, st,
            dp::launch_expand_affine(e->adv_x, e->xf_d, rects, e->net_in, S, n0, n, H, H, e->Cp, e->bf16, st));
+      KERNEL_OK(); ++e->launches;
     } else {
       PROF(e, "expand_k1", (double)n * H * H * 3 * e->es + 7.0 * H * H * 4 * (double)n / S, 0, st,
            dp::launch_expand(nullptr, a->x, a->mask, a->pattern, e->scale, rects, e->net_in, B, S, n0, n, H, H, e->Cp, e->bf16, true, e->num_sms, st));
+      KERNEL_OK(); ++e->launches;
     }
-    KERNEL_OK(); ++e->launches;
-    e->forward(n, e->net_in, true, st);
+    e->forward(n, chunk_in, true, st);
     PROF(e, "cw_k4", 2.0 * n * e->K * 4, 0, st,
          dp::launch_cw(e->logits, e->y_d + n0, e->tg_d + n0, a->confidence, inv_s, e->loss_d + n0, e->preds_d + n0, e->dlogits, n, e->K, st));
     KERNEL_OK(); ++e->launches;
@@ -1145,6 +1183,7 @@ static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t
   if (!a->x || !a->mask || !a->pattern || !a->grad_adv || !a->y_host || !a->targeted_host) fail("null pointer in dp_attack_args");
   const int B = a->B, S = a->S, N = B * S;
   e->ensure_samples(N);
+  if (!a->xform_host) e->ensure_net_in_all(N);
   // per-sample labels / criterion flags / rectangles -> pinned staging.  Layout:
   // [H2D region: ys | tg | rects | xforms][D2H region: results]; the regions never overlap.
   GradLayout L_;
@@ -1375,6 +1414,18 @@ int32_t dp_debug_stem_bwd_reduce(dp_engine* e, const void* dY, const int16_t* re
   DP_CATCH
 }
 
+int32_t dp_debug_k1_tuning(int32_t rows, int32_t sg, int32_t mode) {
+  dp::set_expand_tuning(rows, sg, mode);
+  return 0;
+}
+
+int32_t dp_debug_k1_last(int32_t* out4) {
+  if (!out4) return 1;
+  int v[4]; dp::get_expand_last(v);
+  for (int i = 0; i < 4; ++i) out4[i] = v[i];
+  return 0;
+}
+
 int32_t dp_debug_gn_gemm(dp_engine* e, const void* x, const void* w_nk, const float* stats, const float* gamma, const float* beta,
                          const void* shortcut, void* out, int32_t N, int32_t P, int32_t K, int32_t Nout, void* stream) {
   DP_TRY
@@ -1401,6 +1452,11 @@ int32_t dp_debug_gn(dp_engine* e, const void* x, const void* dy, const void* add
   CUDA_OK(cudaSetDevice(e->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   if (N > e->chunk) fail("dp_debug_gn: N=%d exceeds chunk=%d (statistics scratch)", N, e->chunk);
+  if (y == nullptr) {   // statistics only: the pass in front of the tcgen05 GEMM / the classifier head
+    dp::launch_gn_stats(x, e->gn_partial, stats, N, P, C, e->bf16, st); KERNEL_OK();
+    e->launches += 2;
+    return 0;
+  }
   dp::launch_gn_relu_forward(x, y, gamma, beta, e->gn_partial, stats, N, P, C, e->bf16, st); KERNEL_OK();
   if (dy != nullptr) { dp::launch_gn_relu_backward(dy, x, addend, dx, gamma, beta, stats, e->gn_partial, N, P, C, e->bf16, st, gamma_positive != 0); KERNEL_OK(); }
   e->launches += 4;

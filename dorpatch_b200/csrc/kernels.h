@@ -74,6 +74,8 @@ void launch_paste(const float* x, const float* mask, const float* pattern, float
 // fused==true: reads x/mask/pattern/scale (img ignored); else reads img [B,3,H,W].
 // rects [B*S][4][4] int16 dev or nullptr; samples [n0, n0+n) of the b-major ordering are
 // written to out + (n - n0) * H*W*Cp.
+void set_expand_tuning(int rows, int sg, int mode);
+void get_expand_last(int* out4);   // tile rows, sample groups, grid, resident CTAs/SM of the last K1 launch   // K1 launch-shape / store-path overrides (0 = heuristic / default); sweeps only
 void launch_expand(const float* img, const float* x, const float* mask, const float* pattern, const float* scale,
                    const int16_t* rects, void* out, int B, int S, int n0, int n, int H, int W, int Cp, bool bf16,
                    bool fused, int num_sms, cudaStream_t st);

@@ -128,7 +128,7 @@ struct GemmParams {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(THREADS, 1) gn_gemm_fwd_kernel(GemmParams p) {
+__global__ void __launch_bounds__(THREADS, 2) gn_gemm_fwd_kernel(GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.Nout / BN;
@@ -225,34 +225,50 @@ __global__ void __launch_bounds__(THREADS, 1) gn_gemm_fwd_kernel(GemmParams p) {
       mbar_arrive(bar_full + 8 * stage);
     }
     // ===================== epilogue =====================
-    mbar_wait(bar_acc, 0u);
-    tc_fence_after();
+    // warp w owns TMEM lanes 32w..32w+31 = tile rows; a thread handles one output row, 64 columns per trip: the 8
+    // shortcut loads of a trip are issued together (and the first trip's before the accumulator wait), so the row's
+    // latency is paid once per 64 columns instead of once per 16
     const int m = m0 + warp * 32 + lane;
     const bool live = m < p.M;
     __nv_bfloat16* drow = p.D + (size_t)m * p.Nout + n0;
-    const __nv_bfloat16* rrow = p.R ? p.R + (size_t)m * p.Nout + n0 : nullptr;
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t acc[16];
-      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
-      if (live) {
-        float f[16];
+    const __nv_bfloat16* rrow = (p.R && live) ? p.R + (size_t)m * p.Nout + n0 : nullptr;
+    uint4 rq[8];
+    if (rrow != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(acc[i]);
-        if (rrow != nullptr) {
+      for (int i = 0; i < 8; ++i) rq[i] = *(reinterpret_cast<const uint4*>(rrow) + i);   // plain loads: R may be D (in-place shortcut)
+    }
+    mbar_wait(bar_acc, 0u);
+    tc_fence_after();
+#pragma unroll 1
+    for (int h0 = 0; h0 < BN; h0 += 64) {
+      if (h0 > 0 && rrow != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rq[i] = *(reinterpret_cast<const uint4*>(rrow + h0) + i);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t acc[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(h0 + q * 16), acc);
+        if (live) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(acc[i]);
+          if (rrow != nullptr) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint4 qv = rq[q * 2 + h];
+              const uint32_t w[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { const float2 e = unpack2(w[i]); f[h * 8 + 2 * i] += e.x; f[h * 8 + 2 * i + 1] += e.y; }
+            }
+          }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const uint4 q = *(reinterpret_cast<const uint4*>(rrow + c0) + h);   // plain load: R may be D (in-place shortcut)
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { const float2 e = unpack2(w[i]); f[h * 8 + 2 * i] += e.x; f[h * 8 + 2 * i + 1] += e.y; }
+            uint4 o;
+            o.x = pack2(f[h * 8 + 0], f[h * 8 + 1]); o.y = pack2(f[h * 8 + 2], f[h * 8 + 3]);
+            o.z = pack2(f[h * 8 + 4], f[h * 8 + 5]); o.w = pack2(f[h * 8 + 6], f[h * 8 + 7]);
+            *(reinterpret_cast<uint4*>(drow + h0 + q * 16) + h) = o;
           }
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint4 o;
-          o.x = pack2(f[h * 8 + 0], f[h * 8 + 1]); o.y = pack2(f[h * 8 + 2], f[h * 8 + 3]);
-          o.z = pack2(f[h * 8 + 4], f[h * 8 + 5]); o.w = pack2(f[h * 8 + 6], f[h * 8 + 7]);
-          *(reinterpret_cast<uint4*>(drow + c0) + h) = o;
         }
       }
     }
@@ -310,11 +326,12 @@ __global__ void pack_w_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16
 
 }  // namespace tc
 
-int gn_gemm_tile_n(int Nout) { return Nout >= 256 ? 256 : Nout; }
+// BN <= 128: 101 KB of shared memory and 128 TMEM columns per CTA -> two CTAs per SM, one's epilogue under the other's main loop
+int gn_gemm_tile_n(int Nout) { return Nout >= 128 ? 128 : Nout; }
 
 bool gn_gemm_supported(int P, int K, int Nout) {
   const int bn = gn_gemm_tile_n(Nout);
-  return K % tc::BK == 0 && K >= 64 && (bn == 64 || bn == 128 || bn == 256) && Nout % bn == 0 &&
+  return K % tc::BK == 0 && K >= 64 && (bn == 64 || bn == 128) && Nout % bn == 0 &&
          (tc::BM + P - 1) / P + 1 <= tc::MAX_TILE_SAMPLES;
 }
 
@@ -338,7 +355,6 @@ bool launch_gn_gemm_forward(const void* x, const void* w_packed, const float* st
   switch (bn) {
     GG_CASE(64)
     GG_CASE(128)
-    GG_CASE(256)
     default: return false;
   }
 #undef GG_CASE

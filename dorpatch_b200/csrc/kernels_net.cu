@@ -246,7 +246,7 @@ static int apply_slabs(int P, int C, int V) {
   return s;
 }
 
-void launch_gn_stats(const void* x, float* partial, float* stats, int N, int P, int C, bool bf16, cudaStream_t st) {
+static void launch_gn_stats_v1(const void* x, float* partial, float* stats, int N, int P, int C, bool bf16, cudaStream_t st) {
   const int splits = gn_splits(P, C, bf16);
   DISPATCH_T(bf16, (gn_stats_kernel<T><<<dim3(splits, N), GN_THREADS, 0, st>>>((const T*)x, partial, P, C, splits)));
   DISPATCH_T(bf16, (gn_finalize_kernel<T><<<N, 32, 0, st>>>(partial, stats, P, C, splits)));
@@ -1329,6 +1329,45 @@ __device__ __forceinline__ void group_reduce(const float* a, const float* b, int
   }
 }
 
+// ---- statistics only (the tcgen05 GEMM applies GroupNorm+ReLU in its prologue; the classifier head) -----------------
+// Streaming: grid (tiles, N), a CTA reads one contiguous 64 KB tile of one sample with the linear thread -> vector
+// mapping (16 independent 16-byte loads per thread, two batches of 8 in flight), reduces to the 32 group sums and
+// writes partial[n][tile][group][2]; gn_finalize_kernel adds the tiles in order (deterministic).
+constexpr int ST_TH = 256, ST_ITER = 16, ST_TILE = ST_TH * ST_ITER;   // vectors per tile
+template <typename T>
+__global__ void __launch_bounds__(ST_TH) stats_kernel(const T* __restrict__ x, float* __restrict__ partial, int P, int C, int tiles) {
+  using A = Acc<T>;
+  constexpr int V = A::V;
+  __shared__ float red[(ST_TH / 32) * 64];
+  __shared__ float part[64];
+  const int n = blockIdx.y, tile = blockIdx.x;
+  const uint32_t nvec = (uint32_t)(((size_t)P * C) / V);
+  const uint32_t v0 = (uint32_t)tile * ST_TILE;
+  const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)n * P * C) + v0 + threadIdx.x;
+  const uint32_t left = nvec - v0;                                  // vectors from the tile start to the sample end
+  float a[V], bq[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { a[i] = 0.f; bq[i] = 0.f; }
+#pragma unroll
+  for (int h = 0; h < ST_ITER / 8; ++h) {
+    uint4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t o = (uint32_t)(h * 8 + j) * ST_TH + threadIdx.x;
+      v[j] = o < left ? __ldg(src + (h * 8 + j) * ST_TH) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f[V]; A::unpack(v[j], f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { a[i] += f[i]; bq[i] = fmaf(f[i], f[i], bq[i]); }
+    }
+  }
+  group_reduce<V>(a, bq, C, red, part);
+  __syncthreads();
+  if (threadIdx.x < 64) partial[((size_t)n * tiles + tile) * 64 + threadIdx.x] = part[threadIdx.x];
+}
+
 // ---- forward --------------------------------------------------------------------------------------
 template <typename T, int TH>
 __global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
@@ -2150,6 +2189,18 @@ void launch_gn_relu_backward(const void* dy, const void* x, const void* addend, 
     cudaGetLastError();
   }
   launch_gn_relu_backward_2pass(dy, x, addend, dx, gamma, beta, stats, partial, N, P, C, bf16, st);
+}
+
+void launch_gn_stats(const void* x, float* partial, float* stats, int N, int P, int C, bool bf16, cudaStream_t st) {
+  const int V = bf16 ? 8 : 4, cols = C / V;
+  const size_t nvec = (size_t)P * cols;
+  const int tiles = (int)((nvec + gn2::ST_TILE - 1) / gn2::ST_TILE);
+  if (gn_version() >= 2 && cols <= gn2::ST_TH && gn2::ST_TH % cols == 0 && C % V == 0 && tiles * 64 <= GN_WS_FLOATS_PER_SAMPLE) {
+    DISPATCH_T(bf16, (gn2::stats_kernel<T><<<dim3(tiles, N), gn2::ST_TH, 0, st>>>((const T*)x, partial, P, C, tiles)));
+    DISPATCH_T(bf16, (gn_finalize_kernel<T><<<N, 32, 0, st>>>(partial, stats, P, C, tiles)));
+    return;
+  }
+  launch_gn_stats_v1(x, partial, stats, N, P, C, bf16, st);
 }
 
 }  // namespace dp

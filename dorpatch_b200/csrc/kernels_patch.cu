@@ -120,6 +120,7 @@ struct ExpandParams {
   const float* img; const float* x; const float* mask; const float* pattern; const float* scale;
   const int16_t* rects; void* out;
   int B, S, n0, n, H, W, sgroups, R;
+  int mode;   // 0: bulk stores (cp.async.bulk) for untouched tiles / rows + 16-byte stores for occluded rows; 1: 16-byte stores only
 };
 
 // Shared memory (dynamic): [mbarrier, 512 B][input planes NP*R*W fp32][clean tile R*W*CP T].
@@ -225,7 +226,8 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
           any = any || (rr0[k] < r0 + EXP_R && rr1[k] > r0);
         }
       }
-      if (!any) {                                               // whole tile untouched: one bulk store
+      const bool use_bulk = p.mode == 0;
+      if (!any && use_bulk) {                                   // whole tile untouched: one bulk store
         if (lane == 0) { ptx::bulk_store(dst, clean_b, out_bytes); ptx::bulk_commit(); }
         continue;
       }
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
             rany = rany || cov;
             Z |= cov ? zm[k] : 0u;
           }
-          if (!rany) {                                          // clean row: bulk store
+          if (!rany && use_bulk) {                              // clean row: bulk store
             if (cb == 0 && lane == 0) { ptx::bulk_store(dst + (size_t)rr * row_bytes, clean_b + (size_t)rr * row_bytes, row_bytes); ptx::bulk_commit(); }
             continue;
           }
@@ -298,18 +300,26 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(ExpandParams p) {
 }
 
 // Launch shape.  Work items = images x row tiles (R rows) x sample groups, walked grid-stride by the resident CTAs.
-// The item count of ONE classifier chunk is small (16 images x 28 tiles = 448 at R = 8) and a CTA's cost is dominated
-// by its items' stores, so the grid is chosen for wave efficiency: over the tile heights that divide H and the
-// power-of-two sample-group counts, maximise items / (waves x resident CTAs), residency taken from the occupancy
-// API (round 1 sized the grid from shared memory alone: 448 items on 444 slots = a second wave for 4 CTAs,
-// 0.50 of HBM peak in-step against 0.69 stand-alone).  DORPATCH_K1_ROWS / _K1_SG pin the choice.
+// Measured over tile heights x sample groups x launch sizes (tools/k1_step_sweep.py, profiles/r02_k1_sweep.txt): tiles of
+// 4-8 rows are equivalent and best (a CTA's load + compose prologue stays short and 3-6 CTAs per SM overlap it with their
+// neighbours' stores), 14-16 rows lose 10-30 % (1-2 CTAs per SM, the prologue is exposed), 2 rows lose 15-20 % (per-item
+// overhead), and a launch wants >= 4 items per SM.  Rule: R = 8, or 4 when that leaves fewer than 4 items per SM; sample
+// groups (each re-loads and re-composes the tile) only when the images alone give fewer than 2 items per SM (B = 1).
+// Round 2's first rule maximised "wave efficiency" and picked R = 14 for 512- and 2048-sample launches: 0.29 / 0.65 of
+// peak against 0.72 / 0.79 with R = 8.  DORPATCH_K1_ROWS / _K1_SG (or dp_debug_k1_tuning) pin the choice.
+static int g_k1_rows = -2, g_k1_sg = -1, g_k1_mode = 0;   // launch-shape overrides (environment, or set_expand_tuning for sweeps)
+static int g_k1_last[4] = {0, 0, 0, 0};                    // tile rows, sample groups, grid, resident CTAs per SM of the last launch
+void get_expand_last(int* out4) { for (int i = 0; i < 4; ++i) out4[i] = g_k1_last[i]; }
+void set_expand_tuning(int rows, int sg, int mode) { g_k1_rows = rows < 0 ? 0 : rows; g_k1_sg = sg < 0 ? 0 : sg; g_k1_mode = mode; }
+
 template <typename T, int CP, bool FUSED>
 static void expand_launch(const ExpandParams& p, int num_sms, cudaStream_t st) {
-  static int rows_env = -2, sg_env = -1;
-  if (rows_env == -2) {
-    const char* e = getenv("DORPATCH_K1_ROWS"); rows_env = e ? atoi(e) : 0;
-    const char* g = getenv("DORPATCH_K1_SG"); sg_env = g ? atoi(g) : 0;
+  if (g_k1_rows == -2) {
+    const char* e = getenv("DORPATCH_K1_ROWS"); g_k1_rows = e ? atoi(e) : 0;
+    const char* g = getenv("DORPATCH_K1_SG"); g_k1_sg = g ? atoi(g) : 0;
+    const char* m = getenv("DORPATCH_K1_MODE"); g_k1_mode = m ? atoi(m) : 0;
   }
+  const int rows_env = g_k1_rows, sg_env = g_k1_sg;
   constexpr int NP = FUSED ? 7 : 3;
   auto smem_of = [&](int R) { return (size_t)EXP_HDR + (size_t)NP * R * p.W * 4 + (size_t)R * p.W * CP * sizeof(T); };
   static int occ_cache[33];
@@ -326,38 +336,35 @@ static void expand_launch(const ExpandParams& p, int num_sms, cudaStream_t st) {
     return occ_cache[R];
   };
   const int nb_img = (p.n0 + p.n - 1) / p.S - p.n0 / p.S + 1;
-  int best_R = 0, best_sg = 1, best_grid = 1;
-  double best_score = -1.0;
-  const int cand[] = {16, 14, 8, 7, 4, 2, 1};
-  for (int R : cand) {
-    if (rows_env > 0 && R != rows_env) continue;
-    if (R > 32 || p.H % R != 0 || smem_of(R) > 200 * 1024) continue;
-    const int slots = num_sms * resident(R);
-    const int tiles = p.H / R;
-    for (int sg = 1; sg <= 32 && (sg == 1 || sg * EXP_WARPS <= p.S); sg *= 2) {
-      if (sg_env > 0 && sg != sg_env) continue;
-      const int items = nb_img * tiles * sg;
-      const int waves = (items + slots - 1) / slots;
-      double score = (double)items / ((double)waves * slots);
-      // each sample group re-loads and re-composes the tile; small tiles pay the per-item setup more often
-      for (int q = sg; q > 1; q >>= 1) score *= 0.97;
-      if (R < 7) score *= 0.94;
-      if (score > best_score) { best_score = score; best_R = R; best_sg = sg; best_grid = items < slots ? items : slots; }
-    }
+  auto usable = [&](int R) { return R >= 1 && R <= 32 && p.H % R == 0 && smem_of(R) <= 200 * 1024; };
+  int best_R = 0, best_sg = 1;
+  if (rows_env > 0 && usable(rows_env)) best_R = rows_env;
+  else {
+    const int pref[] = {8, 7, 4, 2, 1};
+    for (int R : pref)
+      if (usable(R)) { if (best_R == 0) best_R = R; if (nb_img * (p.H / R) >= 4 * num_sms || R <= 4) { best_R = R; break; } }
+    if (best_R == 0) best_R = 1;
   }
-  if (best_R == 0) { best_R = 1; best_sg = 1; best_grid = nb_img * p.H; }
+  if (sg_env > 0) best_sg = sg_env;
+  else
+    while (nb_img * (p.H / best_R) * best_sg < 2 * num_sms && best_sg * 2 * EXP_WARPS <= p.S && best_sg < 32) best_sg *= 2;
+  const int items_total = nb_img * (p.H / best_R) * best_sg;
+  const int slots = num_sms * resident(best_R);
+  const int best_grid = items_total < slots ? items_total : slots;
   const size_t smem = smem_of(best_R);
   cudaFuncSetAttribute(expand_kernel<T, CP, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ExpandParams q = p;
   q.R = best_R;
   q.sgroups = best_sg;
+  q.mode = g_k1_mode;
+  g_k1_last[0] = best_R; g_k1_last[1] = best_sg; g_k1_last[2] = best_grid; g_k1_last[3] = resident(best_R);
   expand_kernel<T, CP, FUSED><<<best_grid, EXP_THREADS, smem, st>>>(q);
 }
 
 void launch_expand(const float* img, const float* x, const float* mask, const float* pattern, const float* scale,
                    const int16_t* rects, void* out, int B, int S, int n0, int n, int H, int W, int Cp, bool bf16,
                    bool fused, int num_sms, cudaStream_t st) {
-  ExpandParams p{img, x, mask, pattern, scale, rects, out, B, S, n0, n, H, W, 1, EXP_R_DEFAULT};
+  ExpandParams p{img, x, mask, pattern, scale, rects, out, B, S, n0, n, H, W, 1, EXP_R_DEFAULT, 0};
 #define EXP_CASE(TT, CPV)                                                   \
   if (fused) expand_launch<TT, CPV, true>(p, num_sms, st);                 \
   else expand_launch<TT, CPV, false>(p, num_sms, st)

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DP_ABI_VERSION 5
+#define DP_ABI_VERSION 6
 
 enum dp_precision {
   DP_PREC_FP32 = 0, /* fp32 storage, fp32 FMA math (no tensor cores): parity checks   */
@@ -117,6 +117,9 @@ int32_t dp_expand_dev(dp_engine* e, const float* img, int32_t B, int32_t S, cons
  * (bench.py's roofline leg times this launch). */
 int32_t dp_expand_step_dev(dp_engine* e, const float* x, const float* mask, const float* pattern, int32_t B, int32_t S,
                            const int16_t* rects_dev, int32_t n0, int32_t n, void* out, void* stream);
+/* How many EOT samples one K1 launch of dp_attack_grad covers when the step holds n_samples: all of them (one launch
+ * per step into a step-sized buffer) while that buffer stays under DORPATCH_K1_WHOLE_MB, else one classifier chunk. */
+int32_t dp_k1_samples_per_launch(const dp_engine* e, int32_t n_samples);
 int32_t dp_input_layout(const dp_engine* e, int32_t* c_pad, int32_t* elem_bytes);
 
 /* ---- forward-only: model(occlude(img)) ---------------------------------------------- */
@@ -211,9 +214,15 @@ int32_t dp_failed_set_read(dp_engine* e, int32_t b, int32_t* idx_host_out, int32
  * dp_debug_gn_gemm: the tcgen05 GroupNorm-prologue GEMM on caller-supplied operands: out[m,n] = sum_k
  *   relu(gn(x))[m,k] * W[n,k] (+ shortcut); x [N*P,K] bf16, w_nk [Nout,K] bf16, stats [N,32,2] (mean, rstd), all dev.
  * dp_debug_gn: GroupNorm(32)+ReLU forward (and, with dy, backward-to-input) in the engine's activation dtype on
- *   caller-supplied [N,P,C] tensors; stats [N,32,2] dev out. */
+ *   caller-supplied [N,P,C] tensors; stats [N,32,2] dev out.  y == NULL: statistics pass only (the streaming
+ *   kernel in front of the tcgen05 GEMM and the classifier head). */
 int32_t dp_debug_stem_bwd_reduce(dp_engine* e, const void* dY, const int16_t* rects_host, int32_t B, int32_t S, float* G,
                                  void* stream);
+/* K1 launch-shape sweep hook (tools/k1_step_sweep.py): tile rows / sample groups (0 = the wave-efficiency heuristic) and the
+ * store path (0 = bulk stores + 16-byte stores for occluded rows, 1 = 16-byte stores only).  Process-wide. */
+int32_t dp_debug_k1_tuning(int32_t rows, int32_t sg, int32_t mode);
+/* launch shape of the last K1 launch: {tile rows, sample groups, grid, resident CTAs per SM}. */
+int32_t dp_debug_k1_last(int32_t* out4);
 int32_t dp_debug_gn_gemm(dp_engine* e, const void* x, const void* w_nk, const float* stats, const float* gamma,
                          const float* beta, const void* shortcut, void* out, int32_t N, int32_t P, int32_t K,
                          int32_t Nout, void* stream);

@@ -84,7 +84,15 @@ def test_groupnorm_relu_fwd_bwd_vs_fp64(engines, precision, P, Cc, neg_gamma):
     ey = ((got_y - yr.detach()).abs() * sure).max().item() / yr.abs().max().item()
     edx = ((got_dx - dxr).abs() * sure).max().item() / dxr.abs().max().item()
     mean_ref = x.double().reshape(N, P, 32, Cc // 32).mean((1, 3))
+    rstd_ref = 1.0 / torch.sqrt(x.double().reshape(N, P, 32, Cc // 32).var((1, 3), unbiased=False) + 1e-5)
     assert (stats[:, :, 0].cpu().double() - mean_ref).abs().max().item() <= 1e-4
+    # the statistics-only pass (streaming kernel in front of the tcgen05 GEMM / the classifier head): same (mean, rstd)
+    stats2 = torch.full((N, 32, 2), float("nan"), device=DEV)
+    _lib.check(e.lib.dp_debug_gn(e.handle, _ptr(xd), None, None, _ptr(gd), _ptr(bd), 1, None, None, _ptr(stats2), N, P, Cc, e._stream()))
+    torch.cuda.synchronize()
+    assert (stats2[:, :, 0].cpu().double() - mean_ref).abs().max().item() <= 1e-4
+    assert ((stats2[:, :, 1].cpu().double() - rstd_ref).abs() / rstd_ref).max().item() <= 1e-4
+    assert ((stats[:, :, 1].cpu().double() - rstd_ref).abs() / rstd_ref).max().item() <= 1e-4
     print(precision, P, Cc, "neg" if neg_gamma else "", "rel err y %.2e dx %.2e" % (ey, edx))
     assert ey <= tol and edx <= tol, (ey, edx)
 

@@ -15,7 +15,7 @@ def main():
         print("bench parse failed:", ex)
         return
     print("value", r(a["value"]), a["dtype"], "ms/step", r(a["ms_per_step"], 2), "e2e", r(a["e2e"]["value"]), "launches", a["gpu_launches"],
-          "n_gpus", a["n_gpus"], "clocks", a.get("clocks"))
+          "n_gpus", a["n_gpus"], "host_ms", r(a.get("host_ms_per_step", 0.0), 2), "graph_replays", a.get("graph_replays"), "clocks", a.get("clocks"))
     rf = a.get("roofline")
     if rf:
         print("K1 roofline", {k: r(rf[k], 4) for k in ("frac", "achieved", "ms", "ms_single_launch_event_pair", "samples_per_launch", "unoccluded_gbs") if k in rf})

@@ -24,6 +24,7 @@ def ptr(t):
 def main():
     prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
     img = int(sys.argv[2]) if len(sys.argv) > 2 else 112
+    light = len(sys.argv) > 3 and sys.argv[3] == "light"     # racecheck is ~100x slower: skip the whole-network steps
     torch.cuda.set_device(0)
     dev = "cuda:0"
     B, S = 2, 3
@@ -35,15 +36,23 @@ def main():
     table = PM.universe(img, 2)
     idx = np.random.RandomState(0).randint(0, table.shape[0], (B, S))
     rects = PM.gather(table, idx)
-    y = eng.predict(x).astype(np.int64)
+    y = eng.predict(x).astype(np.int64) if not light else np.array([1, 2])
     G = torch.zeros_like(x)
-    for stage in (0, 1):
+    for stage in (() if light else (0, 1)):
         r = eng.attack_grad(x, m, p, rects, y, [False] * B, 0.1, 4.0, stage, G)
         eng.attack_update(x, m, p, G, np.full(B, 0.01, np.float32), [1e-3] * B, [1e-5] * B, 1e-3, stage)
         assert np.isfinite(r["loss_adv"]).all()
-    eng.predict(x, S, rects)
+    if not light:
+        eng.predict(x, S, rects)
     eng.expand(x, S, rects)
     eng.paste(x, m, p, 4.0)
+    # the in-step K1 variant (paste fused in), both store paths
+    rd = torch.from_numpy(np.ascontiguousarray(rects.reshape(B * S, 4, 4), np.int16)).to(dev)
+    out = torch.empty((B * S, img, img, eng.c_pad), dtype=torch.bfloat16 if eng.elem_bytes == 2 else torch.float32, device=dev)
+    for mode in (0, 1):
+        eng.lib.dp_debug_k1_tuning(0, 0, mode)
+        _lib.check(eng.lib.dp_expand_step_dev(eng.handle, ptr(x), ptr(m), ptr(p), B, S, ptr(rd), 0, B * S, ptr(out), eng._stream()))
+    eng.lib.dp_debug_k1_tuning(0, 0, 0)
     eng.window_sum(m, 7)
     eng.failed_write(0, [1, 5, 9])
     eng.failed_update(idx, [0] * B, [True] * B, loss=np.random.rand(B, S).astype(np.float32))
@@ -61,7 +70,7 @@ def main():
                                        eng._stream()))
     torch.cuda.synchronize()
     eng.close()
-    print("sanitize_run ok", prec, img)
+    print("sanitize_run ok", prec, img, "light" if light else "full")
 
 
 if __name__ == "__main__":
