@@ -340,6 +340,22 @@ class DorPatch(object):
             print(">> %d failures collected!" % len(failed))
             return failed
 
+        def draw(i):                                             # attack.py:193-204 (+ :208-218 dual) for every active image
+            idx = np.zeros((B, S), np.int64)
+            idx2 = np.zeros((B, S), np.int64) if dual else None
+            nff = [0] * B
+            for b, s in enumerate(st):
+                if s.active:
+                    idx[b], nff[b] = s.sample(i, n_mask, S)
+                    if dual:
+                        idx2[b], _ = s.sample(i, n_mask, S)
+            sl = slice(rank * S_loc, (rank + 1) * S_loc)
+            return idx, idx2, nff, _masks.gather(table, idx[:, sl], idx2[:, sl] if dual else None)
+
+        from concurrent.futures import ThreadPoolExecutor
+        sampler = ThreadPoolExecutor(max_workers=1)
+        prefetched = None
+
         for stage in range(2):
             print('============= Stage %d =============' % stage)
             for s in st:
@@ -383,26 +399,28 @@ class DorPatch(object):
                     for b, s in enumerate(st):
                         if s.active:
                             s.set_failed(scan(b, adv_x))
-                idx = np.zeros((B, S), np.int64)
-                idx2 = np.zeros((B, S), np.int64) if dual else None
-                nff = [0] * B
-                for b, s in enumerate(st):
-                    if s.active:
-                        idx[b], nff[b] = s.sample(i, n_mask, S)
-                        if dual:
-                            idx2[b], _ = s.sample(i, n_mask, S)
+                if prefetched is not None and prefetched[0] == (stage, i):
+                    idx, idx2, nff, rects = prefetched[1].result()
+                else:
+                    idx, idx2, nff, rects = draw(i)
+                prefetched = None
+                # Draw step i+1's samples on a helper thread while the GPU runs step i -- only where the reference's RNG
+                # consumption is provably unchanged: the draw depends on nothing this step can alter (i+1 < 1000: no
+                # failed-set samples), the stage does run an iteration i+1, and no image can stop at step i (a stop needs
+                # lr * 0.1 < 1e-3 together with a plateau, i.e. not_decay >= PATIENCE before the step).
+                if (i + 1 < max_iterations and i + 1 < 1000 and
+                        not any(s.active and s.not_decay >= PATIENCE - 1 and float(s.lr) * 0.1 < 1e-3 for s in st)):
+                    prefetched = ((stage, i + 1), sampler.submit(draw, i + 1))
                 if dist and i % 100 == 0:
                     # every rank must have drawn the same indices (same RNG streams): a diverged rank would evaluate a
                     # slice of a different sample set and the gathered losses would be book-kept against the wrong masks
                     _assert_same_on_all_ranks(dist, idx, dev, "EOT sample indices at step %d" % i)
-                sl = slice(rank * S_loc, (rank + 1) * S_loc)
-                rects = _masks.gather(table, idx[:, sl], idx2[:, sl] if dual else None)
                 structured_used = [s.structured for s in st]
                 coeff_used = [s.coeff_group_lasso for s in st]
                 xf = None
                 if use_eot:
                     from . import eot as _eot
-                    xf = _eot.sample(eot_rng, B, S, eot_affine, eot_colour)[:, sl]
+                    xf = _eot.sample(eot_rng, B, S, eot_affine, eot_colour)[:, rank * S_loc:(rank + 1) * S_loc]
                 r = eng.attack_grad(x, adv_mask, adv_pattern, rects, [s.y for s in st],
                                     [s.crit_targeted for s in st], confidence, eps, stage, G, S_total=S, xforms=xf)
                 loss_adv, preds = r["loss_adv"], r["preds"]
@@ -478,6 +496,7 @@ class DorPatch(object):
                     if not s.targeted and last_preds is not None:
                         s.y, sw = _pick_target(last_preds[b], s.y)
                         s.crit_targeted = s.crit_targeted or sw
+        sampler.shutdown(wait=True)
         self.last_stats = dict(steps=steps, samples_per_step=B * S, final_labels=[s.y for s in st])
         return mask_best, pattern_best
 
