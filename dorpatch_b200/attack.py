@@ -148,6 +148,17 @@ class _ImageState(object):
         return improved, bool(self.lr < np.float32(1e-3))
 
 
+def _may_prefetch(states, i, max_iterations):
+    """May step i+1's samples be drawn before step i's bookkeeping without changing the reference's RNG consumption?
+    Yes iff the stage does run an iteration i+1 with the same set of active images and the draw reads nothing step i
+    writes: i+1 < 1000 (no samples from the failed set, attack.py:193-198), i+1 < max_iterations, and no active image can
+    stop at step i -- a stop (attack.py:306-315) needs a plateau (not_decay > PATIENCE after the step, so >= PATIENCE - 1
+    before it, conservatively) whose decayed lr falls below 1e-3 (10 % margin on the float comparison)."""
+    if i + 1 >= max_iterations or i + 1 >= 1000:
+        return False
+    return not any(s.active and s.not_decay >= PATIENCE - 1 and float(s.lr) * 0.1 < 1.1e-3 for s in states)
+
+
 def _pick_target(preds, label):
     """attack.py:106-122 for one image; returns (label, switched)."""
     preds = np.asarray(preds).reshape(-1)
@@ -408,8 +419,7 @@ class DorPatch(object):
                 # consumption is provably unchanged: the draw depends on nothing this step can alter (i+1 < 1000: no
                 # failed-set samples), the stage does run an iteration i+1, and no image can stop at step i (a stop needs
                 # lr * 0.1 < 1e-3 together with a plateau, i.e. not_decay >= PATIENCE before the step).
-                if (i + 1 < max_iterations and i + 1 < 1000 and
-                        not any(s.active and s.not_decay >= PATIENCE - 1 and float(s.lr) * 0.1 < 1e-3 for s in st)):
+                if _may_prefetch(st, i, max_iterations):
                     prefetched = ((stage, i + 1), sampler.submit(draw, i + 1))
                 if dist and i % 100 == 0:
                     # every rank must have drawn the same indices (same RNG streams): a diverged rank would evaluate a
