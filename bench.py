@@ -397,6 +397,42 @@ def run_native(args):
                           "default); bf16 legs are reported under `legs` and are backed by tests/test_gpu_attack_success.py",
     }
 
+    def k1_leg_roofline(eng, wl):
+        """K1 (expand_kernel<FUSED=1>) on the launch shape this workload's step uses: CUDA events around 10 back-to-back launches
+        rotating over > 400 MB of outputs, median of 5; algorithmic bytes = 3*H*W*elem per sample + 7 fp32 planes per image."""
+        import ctypes as C
+        from dorpatch_b200 import _lib
+        B, S_loc, es = wl.B, wl.S_loc, eng.elem_bytes
+        n = int(eng.lib.dp_k1_samples_per_launch(eng.handle, B * S_loc))
+        rects = wl.PM.gather(wl.table, np.stack([np.random.RandomState(b).choice(wl.n_mask, S_loc, replace=False) for b in range(B)]))
+        rd = torch.from_numpy(np.ascontiguousarray(rects.reshape(B * S_loc, 4, 4), np.int16)).to(dev)
+        dt_t = torch.bfloat16 if es == 2 else torch.float32
+        n_rot = max(2, int(400e6 // (n * IMG * IMG * eng.c_pad * es)) + 1)
+        bufs = [torch.empty((n, IMG, IMG, eng.c_pad), dtype=dt_t, device=dev) for _ in range(n_rot)]
+        eng.paste(wl.x, wl.mask, wl.pattern, 4.0)
+        starts = list(range(0, B * S_loc - n + 1, n)) or [0]
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def launch(i):
+            _lib.check(eng.lib.dp_expand_step_dev(eng.handle, C.c_void_p(wl.x.data_ptr()), C.c_void_p(wl.mask.data_ptr()), C.c_void_p(wl.pattern.data_ptr()),
+                                                  B, S_loc, C.c_void_p(rd.data_ptr()), starts[i % len(starts)], n, C.c_void_p(bufs[i % n_rot].data_ptr()), eng._stream()))
+        for i in range(4):
+            launch(i)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            ev0.record()
+            for i in range(10):
+                launch(i)
+            ev1.record()
+            torch.cuda.synchronize()
+            ts.append(ev0.elapsed_time(ev1) / 10)
+        ms = float(np.median(ts))
+        alg = n * IMG * IMG * 3 * es + max(1, n // S_loc) * 7 * IMG * IMG * 4
+        phys = n * IMG * IMG * eng.c_pad * es + max(1, n // S_loc) * 7 * IMG * IMG * 4
+        del bufs
+        return {"frac": alg / ms / 1e6 / pk["hbm"], "frac_physical": phys / ms / 1e6 / pk["hbm"], "achieved_gbs": alg / ms / 1e6, "ms": ms, "samples_per_launch": n, "c_pad": eng.c_pad}
+
     def kernel_table(eng, wl, i):
         eng.profile(True, reset=True)
         wl.step(i)
@@ -543,6 +579,11 @@ def run_native(args):
                 if cfg == "c2" and prec == "bf16":
                     leg["kernels"], leg["kernels_total_ms"] = kernel_table(r["eng"], r["wl"], 900)   # i < 1000: no failed-set sampling (as every timed step)
                 legs["%s_%s" % (prec, cfg)] = leg
+                if cfg in ("c3", "c2"):          # K1 roofline of this leg's in-step launch (same method as the headline `roofline`)
+                    try:
+                        leg["k1_roofline"] = k1_leg_roofline(r["eng"], r["wl"])
+                    except Exception as ex:
+                        leg["k1_roofline"] = {"error": str(ex)[:200]}
                 del r
             except Exception as ex:
                 legs["%s_%s" % (prec, cfg)] = {"error": str(ex)[:300]}

@@ -24,6 +24,8 @@
 #include <tuple>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: no-ops unless a profiler injects itself (ncu --nvtx, nsys)
+
 #include "../../include/dorpatch.h"
 #include "kernels.h"
 
@@ -64,6 +66,14 @@ constexpr int DEPTHS[4] = {3, 4, 6, 3};
 constexpr int WIDTHS[4] = {256, 512, 1024, 2048};
 constexpr int STEM_CH = 64;
 constexpr int STEM_SUB = 128;   // samples per cuDNN stem-conv call
+// NVTX range around the phases of the hot loop (host side; inside a graph capture they mark the capture, not the replay)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 constexpr int UNIT = 7;   // basic_unit of the group lasso / patch selection (attack.py:52)
 
 struct ConvW {            // one convolution's weights (device, KRSC, activation dtype)
@@ -638,6 +648,7 @@ struct dp_engine {
   // ---- classifier forward ------------------------------------------------------------------
   // input: [N,H,H,Cp] T.  train: keep what backward needs.  Leaves logits in `logits`.
   void forward(int N, const void* input, bool train, cudaStream_t st) {
+    NvtxRange nvtx_("dorpatch.classifier_forward");
     if (!weights_loaded) fail("dp_engine_load_weights has not been called");
     if (N > chunk) fail("forward: N=%d exceeds chunk=%d", N, chunk);
     CUDNN_OK(cudnnSetStream(cudnn, st));
@@ -722,6 +733,7 @@ struct dp_engine {
   bool fused_pool_bwd = false;     // ... && DORPATCH_POOL_BWD == "fused": max-pool backward fused in as well (slower, off)
   bool stem_bwd_fused_ok() const { return fused_stem_bwd; }
   void backward(int N, const float* dlog, cudaStream_t st, const FusedReduce* fused = nullptr) {
+    NvtxRange nvtx_("dorpatch.classifier_backward");
     CUDNN_OK(cudnnSetStream(cudnn, st));
     const Block& last = blocks.back();
     const int pl = last.hout * last.hout;
@@ -1048,6 +1060,7 @@ int32_t dp_predict(dp_engine* e, const float* img, int32_t B, int32_t S, const i
                    float* logits_host, void* stream) {
   DP_TRY
   if (!e) fail("null engine");
+  NvtxRange nvtx_("dorpatch.predict");
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_OK(cudaSetDevice(e->cfg.device));
   const int N = B * S;
@@ -1177,6 +1190,7 @@ static void attack_grad_enqueue(dp_engine* e, const dp_attack_args* a, const Gra
 }
 
 static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t st) {
+  NvtxRange nvtx_("dorpatch.attack_grad");
   if (!a) fail("null args");
   e->check_B(a->B);
   if (a->S < 1 || a->S_total < a->S) fail("bad S=%d / S_total=%d", a->S, a->S_total);
@@ -1256,6 +1270,7 @@ static void attack_grad_impl(dp_engine* e, const dp_attack_args* a, cudaStream_t
 }
 
 static void attack_update_impl(dp_engine* e, const dp_update_args* u, cudaStream_t st) {
+  NvtxRange nvtx_("dorpatch.attack_update");
   if (!u) fail("null args");
   e->check_B(u->B);
   if (!u->x || !u->mask || !u->pattern || !u->grad_adv || !u->lr_host || !u->structured_host) fail("null pointer in dp_update_args");

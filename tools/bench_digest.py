@@ -29,7 +29,7 @@ def main():
         if key in a:
             print(key, {q: r(w, 2) for q, w in a[key].items() if q != "note"} if isinstance(a[key], dict) else r(a[key]))
     for name, leg in a.get("legs", {}).items():
-        print("leg", name, {q: r(w, 2) for q, w in leg.items() if q not in ("kernels", "config")})
+        print("leg", name, {q: (r(w, 2) if not isinstance(w, dict) else {a: r(b, 3) for a, b in w.items()}) for q, w in leg.items() if q not in ("kernels", "config")})
         if "kernels" in leg:
             for n, v in list(leg["kernels"].items())[:10]:
                 print("   %-18s %8.3f ms  share %.3f  %s" % (n, v["ms"], v["share"], v.get("frac_of_hbm_peak", v.get("frac_of_bf16_peak"))))
