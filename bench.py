@@ -446,6 +446,9 @@ def run_native(args):
             if v["flops"] > 0 and ("conv" in k or "gemm" in k):
                 d["tflops"] = round(v["flops"] / v["ms"] / 1e9, 1)
                 d["frac_of_bf16_peak"] = round(v["flops"] / v["ms"] / 1e9 / pk["tf_burst"], 3)
+                if v["bytes"] > 0:        # these layers are HBM-bound in this network (33 FLOP/B): the byte rate is the telling one
+                    d["gbs_algorithmic"] = round(v["bytes"] / v["ms"] / 1e6, 1)
+                    d["frac_of_hbm_peak"] = round(v["bytes"] / v["ms"] / 1e6 / pk["hbm"], 3)
             else:
                 d["gbs_algorithmic"] = round(v["bytes"] / v["ms"] / 1e6, 1)
                 d["frac_of_hbm_peak"] = round(v["bytes"] / v["ms"] / 1e6 / pk["hbm"], 3)

@@ -864,7 +864,7 @@ int32_t dp_engine_create(const dp_config* cfg, dp_engine** out) {
     const char* sb_env = getenv("DORPATCH_STEM_BWD");
     e->fused_stem_bwd = e->own_stem && !(sb_env && strcmp(sb_env, "cudnn") == 0);
     const char* fg_env = getenv("DORPATCH_FUSED_GEMM");
-    e->fused_gemm = e->bf16 && fg_env && atoi(fg_env) != 0;   // not validated on hardware yet: off unless asked for
+    e->fused_gemm = e->bf16 && fg_env && atoi(fg_env) != 0;   // validated on hardware (tests/test_gpu_ops.py, test_gpu_fused_gemm.py) but 2x slower than cublasLt + GroupNorm: off unless asked for
     if (const char* g_env = getenv("DORPATCH_GRAPH")) e->graphs_on = atoi(g_env) != 0;
     if (const char* k_env = getenv("DORPATCH_K1_WHOLE_MB")) e->k1_whole_max = (size_t)std::max(0, atoi(k_env)) << 20;
     const char* pb_env = getenv("DORPATCH_POOL_BWD");
