@@ -16,12 +16,16 @@ all-reduce of the patch gradient per step).
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = the same step through host buffers
 (H2D of x/mask/pattern + D2H of mask/pattern/losses every step, dp_attack_step_host), `roofline` = the hand-written K1
-kernel, timed on the variant and launch shape the step itself uses, against the measured HBM copy bandwidth,
-`kernels` = per-category device time / achieved rate of one profiled step, `cpu_baseline` = the oracle port of the
-reference's step on this box's host cores.  Extra legs (N=1 only; `legs`): the same step at bf16, configs[1] ("c2",
+kernel, timed on the variant and launch shape the step itself uses (one launch per step), against the measured HBM copy
+bandwidth: `frac` counts the algorithmic bytes (3 channels), `frac_physical` the bytes really moved (the fp32 / tf32 network
+input carries a zero pad channel for the library stem), `traffic` the DRAM bytes of that launch from the last ncu capture
+(profiles/k1_traffic.json); `kernels` = per-category device time / achieved byte and flop rates of one profiled step,
+`host_ms_per_step` = host time the GPU waits for, `graph_replays` = CUDA-graph replays of dp_attack_grad so far,
+`cpu_baseline` = the oracle port of the reference's step on this box's host cores.  Extra legs (N=1 only; `legs`): the same step at bf16, configs[1] ("c2",
 32 x 16) at both precisions, the reference's default shape (1 image x 128 EOT), the stage-0 step of configs[4]
 ("c5": targeted, 10 % budget, density + group-lasso regularisers live), PatchCleanser evaluation throughput, and the
-scan-amortised throughput (the reference re-scans the whole mask universe every 100 steps, attack.py:187-190).
+scan-amortised throughput (the reference re-scans the whole mask universe every 100 steps, attack.py:187-190); the c3 / c2
+legs carry the K1 roofline of their own launch shape (`k1_roofline`).  `--config c5s0 --gpus 4` = configs[4] on 4 GPUs.
 """
 import argparse
 import json
